@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the gbx-lm quantized-matmul hot path on B200.
+
+Metric (BASELINE.json): "4-bit qmatmul HBM GB/s (M=1) & decode tok/s, Llama-3-8B, 1-8 B200".
+
+One STEP = one decode token through the quantized-matmul path of the workload: the 7*L
+`QuantizedLinear` forwards (q,k,v,o,gate,up,down of every block) at M = batch rows, on synthetic
+layer-mix weights.  `value` = ALGORITHMIC bytes of a step (packed weights + scales +
+biases + x + y) / device time of a step, inputs resident in HBM, the step
+replayed from a CUDA graph.  The body of Llama-3-8B (3.4 GB) is 27x the 126 MB L2, so every step
+streams its weights from HBM (L2 defeated by input size).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl gbxq|reference]
+                    [--model llama-3-8b] [--strategy bpw-4.0] [--batch 1]
+
+N > 1 (launched by torch.distributed.run): tensor-parallel shards of the same model (strong scaling):
+column-parallel q/k/v/gate/up, row-parallel o/down followed by a sum all-reduce.
+`--impl reference` times the CPU restatement of the reference path (oracle/, OpenMP over all host
+cores; MLX itself is not installable here -- DESIGN.md) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "qmatmul_hbm_gbs_m1"
+UNIT = "GB/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle-reason sampler running during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_plan(args):
+    from gbx_lm_b200 import workloads as W
+
+    dims = W.MODELS[args.model]
+    strat = None if args.strategy == "uniform" else W.STRATEGIES[args.strategy](dims.layers)
+    plan = W.layer_plan(dims, strat, args.bits, args.group_size)
+    return dims, plan
+
+
+def shard_plan(plan, tp: int):
+    """TP shard shapes: column-parallel splits N, row-parallel (o_proj, down_proj) splits K."""
+    out = []
+    for (i, p, n, k, b, g) in plan:
+        if p in ("o_proj", "down_proj"):
+            assert k % tp == 0 and (k // tp) % g == 0 and ((k // tp) * b) % 32 == 0
+            out.append((i, p, n, k // tp, b, g))
+        else:
+            assert n % tp == 0
+            out.append((i, p, n // tp, k, b, g))
+    return out
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_gbxq(args):
+    import torch
+    import torch.distributed as dist
+
+    from gbx_lm_b200 import QuantizedLinear, ops
+    from gbx_lm_b200 import workloads as W
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    dims, plan = build_plan(args)
+    full_plan = plan
+    plan = shard_plan(plan, world) if world > 1 else plan
+    M = args.batch
+
+    # ---- synthetic weights created directly in HBM (seeded); SURVEY.md 8d recipe
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    layers = []
+    for (i, p, n, k, b, g) in plan:
+        m = QuantizedLinear(k, n, bias=False, group_size=g, bits=b)
+        nb = (1 << b) - 1
+        qw = torch.randint(-(2 ** 31), 2 ** 31 - 1, (n, k * b // 32), generator=gen, device=dev, dtype=torch.int64).to(torch.int32).view(torch.uint32)
+        s = ((torch.rand((n, k // g), generator=gen, device=dev) + 0.5) * (2.0 / (k ** 0.5) / nb)).to(torch.bfloat16)
+        eps = torch.rand((n, k // g), generator=gen, device=dev) * 0.1 - 0.05
+        z = (-s.float() * (nb / 2.0) * (1.0 + eps)).to(torch.bfloat16)
+        m._set("qweight", qw)
+        m._set("scales", s)
+        m._set("zeros", z)
+        m._set("channel_scale", None)
+        layers.append((p, m))
+    xbuf = {}
+    for (_, _, n, k, _, _) in plan:
+        if k not in xbuf:
+            xbuf[k] = torch.randn((M, k), generator=gen, device=dev).to(torch.bfloat16)
+    h_in = torch.randn((M, dims.hidden)).to(torch.bfloat16).pin_memory()
+    h_out = torch.empty((M, dims.hidden), dtype=torch.bfloat16).pin_memory()
+    x_hidden = xbuf[dims.hidden]
+
+    outs = [None]
+
+    def step():
+        y = None
+        for p, m in layers:
+            y = m(xbuf[m.input_dims])
+            if world > 1 and p in ("o_proj", "down_proj"):
+                dist.all_reduce(y)
+        outs[0] = y
+
+    # ---- warm-up eagerly (also sets kernel attributes), then capture one step into a CUDA graph
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        step()
+        step()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    n0 = ops.launch_count()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step()
+    launches_per_step = ops.launch_count() - n0
+    y_last = outs[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        graph.replay()
+    barrier()
+
+    # ---- timed region: EXACTLY K steps, CUDA events on the launching stream, max over ranks
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        graph.replay()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+
+    # ---- e2e: the same step through the public API with HOST buffers (pinned), copies inside the timed region
+    def e2e_step():
+        x_hidden.copy_(h_in, non_blocking=True)
+        graph.replay()
+        h_out.copy_(y_last if y_last.shape == h_out.shape else y_last[:, : dims.hidden], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    f1.record()
+    barrier()
+    e2e_wall = (time.perf_counter() - t0) * 1e3 / args.steps
+    e2e_ms = max(f0.elapsed_time(f1) / args.steps, e2e_wall)  # host-visible time per step (>= device time)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+
+    bytes_step = sum(W.qmm_bytes(M, n, k, b, g) for (_, _, n, k, b, g) in full_plan)
+    value = bytes_step / (ms_step * 1e-3) / 1e9
+    peak, peak_src = load_peaks()
+    # roofline of the dominant kernel (the streaming GEMV: every launch of the timed region is one):
+    # per-launch algorithmic bytes / per-launch average duration == per-rank bytes / step time
+    rank_bytes = sum(W.qmm_bytes(M, n, k, b, g) for (_, _, n, k, b, g) in plan)
+    achieved = rank_bytes / (ms_step * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 5), "higher_is_better": True,
+        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {
+            "workload": f"{args.model} layer-mix {args.strategy} decode batch {M}: {len(full_plan)} QuantizedLinear "
+                        f"forwards/step (stored bpw {W.stored_bpw(full_plan):.3f})",
+            "bytes_per_step": bytes_step, "l2": "inputs larger than L2 (weights per step >> 126 MB)",
+            "parallelism": f"tp{world}" if world > 1 else "single", "launch": "cuda_graph",
+        },
+        "decode_tok_s_qmm_only": round(1e3 / ms_step * M, 2),
+        "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                     "kernel": "gbxq::gemv_kernel (all launches of the step)",
+                     "bytes_per_launch_avg": rank_bytes // len(plan),
+                     "avg_launch_us": round(ms_step * 1e3 / max(launches_per_step, 1), 3)},
+        "e2e": {"value": round(bytes_step / (e2e_ms * 1e-3) / 1e9, 2), "unit": UNIT,
+                "h2d_bytes_per_step": int(h_in.numel() * 2), "d2h_bytes_per_step": int(h_out.numel() * 2),
+                "ms_per_step": round(e2e_ms, 5), "wall_ms_per_step": round(e2e_wall, 5)},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_sample(args, layers_for_cpu=[(p, m) for (p, m) in layers[:7]], M=M, budget_s=args.cpu_seconds)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_sample(args, layers_for_cpu=None, M=1, budget_s=12.0):
+    """Times the CPU restatement of the reference path (oracle/gbxq_oracle.c, OpenMP) on a bounded
+    sample: the 7 projections of block 0 of the workload, repeated until ~budget_s seconds."""
+    import numpy as np
+
+    from gbx_lm_b200 import workloads as W
+    from oracle import c_oracle as C
+    from oracle import mlx_affine as A
+
+    dims, plan = build_plan(args)
+    block0 = [e for e in plan if e[0] == 0]
+    data = []
+    if layers_for_cpu is not None:
+        import torch
+
+        for (p, m) in layers_for_cpu:
+            data.append((m.qweight.cpu().view(torch.int32).numpy().view(np.uint32),
+                         m.scales.cpu().view(torch.int16).numpy().view(np.uint16),
+                         m.zeros.cpu().view(torch.int16).numpy().view(np.uint16), m.bits, m.group_size))
+    else:
+        for (i, p, n, k, b, g) in block0:
+            L = A.synth_layer(n, k, b, g, seed=i * 7 + len(data))
+            data.append((L["qweight"], L["scales"], L["zeros"], b, g))
+    xs = {k: A.synth_x(M, k, seed=3) for k in {d[0].shape[1] * 32 // d[3] for d in data}}
+    threads = C.max_threads()
+    nbytes = sum(W.qmm_bytes(M, d[0].shape[0], d[0].shape[1] * 32 // d[3], d[3], d[4]) for d in data)
+
+    def one_pass():
+        for (qw, s, z, b, g) in data:
+            C.qmm_fast(xs[qw.shape[1] * 32 // b], qw, s, z, g, b, nthreads=threads)
+
+    one_pass()  # warm
+    passes, t0 = 0, time.perf_counter()
+    while True:
+        one_pass()
+        passes += 1
+        el = time.perf_counter() - t0
+        if el >= budget_s or passes >= 200:
+            break
+    per = el / passes
+    return {"value": round(nbytes / per / 1e9, 3), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"block 0 of {args.model} {args.strategy} (7 projections, M={M}), {passes} passes in {el:.1f} s, "
+                      f"C/OpenMP restatement of MLX's CPU quantized_matmul (oracle/gbxq_oracle.c)",
+            "ms_per_sample": round(per * 1e3, 3)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from gbx_lm_b200 import workloads as W
+
+    dims, plan = build_plan(args)
+    per_step_budget = max(1.0, min(8.0, 120.0 / max(args.steps + args.warmup, 1)))
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_sample(args, None, args.batch, budget_s=per_step_budget)
+        if i >= args.warmup:
+            vals.append(r)
+    v = statistics.median([r["value"] for r in vals])
+    ms = statistics.median([r["ms_per_sample"] for r in vals])
+    bytes_step = sum(W.qmm_bytes(args.batch, n, k, b, g) for (_, _, n, k, b, g) in plan)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(bytes_step / (v * 1e9) * 1e3, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{args.model} layer-mix {args.strategy} decode batch {args.batch} (CPU: block-0 sample per step)",
+                   "bytes_per_step": bytes_step, "parallelism": "host threads"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": vals[-1]["cores"], "kind": "port", "sample": vals[-1]["sample"]},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "MLX (the reference's numerical backend) is not installable offline; this is the C/OpenMP restatement of its "
+                "CPU quantized_matmul, ms_per_step extrapolated from the sampled block to the whole step",
+        "ms_per_sample": ms,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="gbxq", choices=["gbxq", "reference"])
+    ap.add_argument("--model", default="llama-3-8b")
+    ap.add_argument("--strategy", default="bpw-4.0", choices=["bpw-4.0", "bpw-2.2", "uniform"])
+    ap.add_argument("--bits", type=int, default=4)
+    ap.add_argument("--group-size", type=int, default=64)
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gbxq(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,87 @@
+"""ctypes binding of libgbxq.so (include/gbxq.h).  There is NO fallback: if the CUDA library is
+missing or fails to load, importing the ops raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgbxq.so")
+
+BF16, F16, F32 = 0, 1, 2
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_GEMV, KERNEL_GEMM = 0, 1, 2, 3
+AR_MAX_CTAS = 32
+
+EXPORTS = (
+    "gbxq_abi_version",
+    "gbxq_status_string",
+    "gbxq_last_cuda_error",
+    "gbxq_last_cuda_error_string",
+    "gbxq_qmm",
+    "gbxq_qmm_ex",
+    "gbxq_workspace_bytes",
+    "gbxq_dequantize",
+    "gbxq_select_kernel",
+    "gbxq_launch_count",
+    "gbxq_allreduce_oneshot",
+)
+
+
+class GbxqError(RuntimeError):
+    def __init__(self, status: int, where: str):
+        lib = get()
+        msg = lib.gbxq_status_string(status).decode()
+        if status == -7:
+            msg += ": " + lib.gbxq_last_cuda_error_string().decode()
+        super().__init__(f"{where}: {msg} (status {status})")
+        self.status = status
+
+
+class GbxqValueError(GbxqError, ValueError):
+    """Argument errors surface as ValueError, like MLX's quantized_matmul/dequantize."""
+
+
+_lib = None
+
+
+def get() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m gbx_lm_b200.build` (needs nvcc). "
+            "gbx_lm_b200 has no CPU or PyTorch fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i64, ci, u32, sz = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_uint32, ctypes.c_size_t
+    lib.gbxq_abi_version.restype = ci
+    lib.gbxq_status_string.restype = ctypes.c_char_p
+    lib.gbxq_status_string.argtypes = [ci]
+    lib.gbxq_last_cuda_error.restype = ci
+    lib.gbxq_last_cuda_error_string.restype = ctypes.c_char_p
+    lib.gbxq_qmm.restype = ci
+    lib.gbxq_qmm.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, ci, ci, ci, vp, sz, vp]
+    lib.gbxq_qmm_ex.restype = ci
+    lib.gbxq_qmm_ex.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, ci, ci, ci, ci, vp, sz, vp]
+    lib.gbxq_workspace_bytes.restype = sz
+    lib.gbxq_workspace_bytes.argtypes = [i64, i64, i64, ci, ci, ci]
+    lib.gbxq_dequantize.restype = ci
+    lib.gbxq_dequantize.argtypes = [vp, vp, vp, vp, i64, i64, ci, ci, ci, vp]
+    lib.gbxq_select_kernel.restype = ci
+    lib.gbxq_select_kernel.argtypes = [i64, i64, i64, ci, ci, ci]
+    lib.gbxq_launch_count.restype = ctypes.c_uint64
+    lib.gbxq_allreduce_oneshot.restype = ci
+    lib.gbxq_allreduce_oneshot.argtypes = [vp, vp, i64, ci, vp, vp, i64, ci, ci, u32, vp]
+    if lib.gbxq_abi_version() != 1:
+        raise ImportError("libgbxq.so ABI version mismatch; rebuild with `python -m gbx_lm_b200.build --force`")
+    _lib = lib
+    return lib
+
+
+def check(status: int, where: str) -> None:
+    if status == 0:
+        return
+    if status in (-1, -2, -3, -4, -5, -6):
+        raise GbxqValueError(status, where)
+    raise GbxqError(status, where)

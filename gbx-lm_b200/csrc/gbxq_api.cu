@@ -1,0 +1,138 @@
+// gbxq_api.cu -- extern "C" entry points of libgbxq.so (include/gbxq.h): validation + dispatch.
+// Replaces the reference's calls into the MLX extension at
+// gbx_lm/models/quantized_linear_gba.py:195-205 (quantized_matmul + bias) and
+// gbx_lm/tuner/lora.py:62-68 (dequantize).
+#include <atomic>
+
+#include "gbxq_common.cuh"
+
+namespace gbxq {
+
+thread_local cudaError_t g_last_cuda_error = cudaSuccess;
+static std::atomic<uint64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int device_sm_count() {
+    // per-device cache (the library may be used from several devices of one process)
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int v = cache[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cache[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
+// M above which the tensor-core kernel takes over from the streaming GEMV.  The GEMV re-streams
+// the weights once per 2 tokens, the GEMM dequantises each weight once per <=256 tokens.
+static constexpr int64_t kGemvMaxM = 4;
+
+static int select(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype, const void* x, const void* w,
+                  const void* y) {
+    const bool gemv_ok = gemv_supported(M, N, K, bits, gs, dtype, x, w, y);
+    const bool gemm_ok = gemm_supported(M, N, K, bits, gs, dtype, x, w, y);
+    if (gemv_ok && (M <= kGemvMaxM || !gemm_ok)) return GBXQ_KERNEL_GEMV;
+    if (gemm_ok) return GBXQ_KERNEL_GEMM;
+    return GBXQ_KERNEL_GENERIC;
+}
+
+}  // namespace gbxq
+
+using namespace gbxq;
+
+extern "C" {
+
+int gbxq_abi_version(void) { return GBXQ_ABI_VERSION; }
+
+const char* gbxq_status_string(int status) {
+    switch (status) {
+        case GBXQ_OK: return "ok";
+        case GBXQ_EINVAL_BITS: return "bits must be one of 2, 3, 4, 6, 8";
+        case GBXQ_EINVAL_GROUP: return "group_size must be 32, 64 or 128";
+        case GBXQ_ESHAPE: return "inconsistent shapes (need K % 32 == 0, K % group_size == 0, sizes >= 0)";
+        case GBXQ_EDTYPE: return "dtype must be 0 (bf16), 1 (f16) or 2 (f32)";
+        case GBXQ_EALIGN: return "pointer alignment (x, y, qweight, w_out need 16 bytes)";
+        case GBXQ_ENULL: return "required pointer is NULL";
+        case GBXQ_ECUDA: return "CUDA runtime error (see gbxq_last_cuda_error_string)";
+        case GBXQ_EWORKSPACE: return "workspace too small";
+        case GBXQ_EUNSUPPORTED: return "kernel family does not support these arguments";
+    }
+    return "unknown status";
+}
+
+int gbxq_last_cuda_error(void) { return (int)g_last_cuda_error; }
+const char* gbxq_last_cuda_error_string(void) { return cudaGetErrorString(g_last_cuda_error); }
+uint64_t gbxq_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+size_t gbxq_workspace_bytes(int64_t, int64_t, int64_t, int, int, int) { return 0; }
+
+int gbxq_select_kernel(int64_t M, int64_t N, int64_t K, int bits, int group_size, int dtype) {
+    const int rc = validate(M, N, K, bits, group_size, dtype);
+    if (rc != GBXQ_OK) return rc;
+    // alignment-agnostic answer: assume 16-byte aligned tensors
+    return select(M, N, K, bits, group_size, dtype, (const void*)16, (const void*)16, (const void*)16);
+}
+
+int gbxq_qmm_ex(const void* x, const uint32_t* qweight, const void* scales, const void* biases, const void* bias,
+                void* y, int64_t M, int64_t N, int64_t K, int bits, int group_size, int dtype, int kernel,
+                void* workspace, size_t workspace_bytes, void* stream) {
+    (void)workspace;
+    (void)workspace_bytes;
+    const int rc = validate(M, N, K, bits, group_size, dtype);
+    if (rc != GBXQ_OK) return rc;
+    if (M == 0 || N == 0) return GBXQ_OK;
+    if (!x || !qweight || !scales || !biases || !y) return GBXQ_ENULL;
+    const size_t esz = dtype == GBXQ_F32 ? 4 : 2;
+    if (((uintptr_t)x | (uintptr_t)y | (uintptr_t)scales | (uintptr_t)biases | (uintptr_t)bias) & (esz - 1))
+        return GBXQ_EALIGN;
+    if ((uintptr_t)qweight & 3) return GBXQ_EALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    int k = kernel;
+    if (k == GBXQ_KERNEL_AUTO) k = select(M, N, K, bits, group_size, dtype, x, qweight, y);
+    switch (k) {
+        case GBXQ_KERNEL_GENERIC:
+            return launch_generic(x, qweight, scales, biases, bias, y, M, N, K, bits, group_size, dtype, st);
+        case GBXQ_KERNEL_GEMV:
+            if (!gemv_supported(M, N, K, bits, group_size, dtype, x, qweight, y)) return GBXQ_EUNSUPPORTED;
+            return launch_gemv(x, qweight, scales, biases, bias, y, M, N, K, bits, group_size, st);
+        case GBXQ_KERNEL_GEMM:
+            if (!gemm_supported(M, N, K, bits, group_size, dtype, x, qweight, y)) return GBXQ_EUNSUPPORTED;
+            return launch_gemm(x, qweight, scales, biases, bias, y, M, N, K, bits, group_size, st);
+    }
+    return GBXQ_EUNSUPPORTED;
+}
+
+int gbxq_qmm(const void* x, const uint32_t* qweight, const void* scales, const void* biases, const void* bias,
+             void* y, int64_t M, int64_t N, int64_t K, int bits, int group_size, int dtype, void* workspace,
+             size_t workspace_bytes, void* stream) {
+    return gbxq_qmm_ex(x, qweight, scales, biases, bias, y, M, N, K, bits, group_size, dtype, GBXQ_KERNEL_AUTO,
+                       workspace, workspace_bytes, stream);
+}
+
+int gbxq_dequantize(const uint32_t* qweight, const void* scales, const void* biases, void* w_out, int64_t N,
+                    int64_t K, int bits, int group_size, int dtype, void* stream) {
+    const int rc = validate(0, N, K, bits, group_size, dtype);
+    if (rc != GBXQ_OK) return rc;
+    if (N == 0) return GBXQ_OK;
+    if (!qweight || !scales || !biases || !w_out) return GBXQ_ENULL;
+    if (((uintptr_t)w_out & 15) || ((uintptr_t)qweight & 3)) return GBXQ_EALIGN;
+    return launch_dequantize(qweight, scales, biases, w_out, N, K, bits, group_size, dtype, (cudaStream_t)stream);
+}
+
+int gbxq_allreduce_oneshot(const void* in, void* out, int64_t count, int dtype, void* const* peer_bufs_dev,
+                           uint32_t* const* peer_flags_dev, int64_t capacity, int rank, int world, uint32_t seq,
+                           void* stream) {
+    if (dtype < 0 || dtype > 2) return GBXQ_EDTYPE;
+    if (count < 0 || world < 1 || world > 8 || rank < 0 || rank >= world || capacity < 2 * count) return GBXQ_ESHAPE;
+    if (count == 0) return GBXQ_OK;
+    if (!in || !out || !peer_bufs_dev || !peer_flags_dev) return GBXQ_ENULL;
+    if (((uintptr_t)in | (uintptr_t)out) & 15) return GBXQ_EALIGN;
+    const size_t esz = dtype == GBXQ_F32 ? 4 : 2;
+    if (((capacity / 2) * esz) % 16) return GBXQ_EALIGN;
+    return launch_allreduce_oneshot(in, out, count, dtype, peer_bufs_dev, peer_flags_dev, capacity, rank, world, seq,
+                                    (cudaStream_t)stream);
+}
+
+}  // extern "C"

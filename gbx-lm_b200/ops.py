@@ -1,0 +1,185 @@
+"""PyTorch operators over the C ABI: `quantized_matmul` and `dequantize` with the signatures of
+the MLX calls they replace.
+
+    mx.quantized_matmul(x, w, scales, biases, transpose=True, group_size=64, bits=4)
+        -- gbx_lm/models/quantized_linear_gba.py:195-203
+    mx.dequantize(w, scales, biases, group_size=64, bits=4)
+        -- gbx_lm/tuner/lora.py:62-68, gbx_lm/tuner/utils.py:214-220
+
+Registered as torch custom ops `gbxq::qmm` / `gbxq::dequantize` (fake kernels for shape
+propagation, CUDA-graph capturable: the library only enqueues on the current stream).
+CUDA only -- there is deliberately no CPU implementation."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+_DT = {torch.bfloat16: _lib.BF16, torch.float16: _lib.F16, torch.float32: _lib.F32}
+_KERNELS = {"auto": 0, "generic": 1, "gemv": 2, "gemm": 3}
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise ValueError(f"[quantized_matmul] activations/scales must be bf16, f16 or f32, got {t.dtype}") from None
+
+
+def _as_u32_ptr_tensor(w: torch.Tensor) -> torch.Tensor:
+    # checkpoints hold uint32; torch kernels are sparse for uint32, so int32 views are accepted too
+    if w.dtype not in (torch.uint32, torch.int32):
+        raise ValueError(f"[quantized_matmul] qweight must be uint32, got {w.dtype}")
+    return w
+
+
+def _require_cuda(*ts: Optional[torch.Tensor]) -> torch.device:
+    dev = None
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(
+                "gbx_lm_b200 ops run on CUDA (sm_100a) only; there is no CPU fallback. Got a tensor on "
+                f"{t.device}."
+            )
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError("all tensors must live on the same CUDA device")
+    return dev
+
+
+def _check_shapes(w, scales, biases, group_size: int, bits: int, k_x: Optional[int]) -> tuple[int, int]:
+    if bits not in (2, 3, 4, 6, 8):
+        raise ValueError(f"[quantized_matmul] bits must be one of 2, 3, 4, 6, 8; got {bits}")
+    if group_size not in (32, 64, 128):
+        raise ValueError(f"[quantized_matmul] group_size must be 32, 64 or 128; got {group_size}")
+    if w.dim() != 2 or scales.dim() != 2 or scales.shape != biases.shape:
+        raise ValueError("[quantized_matmul] qweight/scales/biases must be 2-D, scales.shape == biases.shape")
+    n = w.shape[0]
+    if (w.shape[1] * 32) % bits:
+        raise ValueError("[quantized_matmul] qweight last dim incompatible with bits")
+    k = w.shape[1] * 32 // bits
+    if scales.shape[0] != n or scales.shape[1] * group_size != k:
+        raise ValueError(
+            f"[quantized_matmul] shapes disagree: qweight {tuple(w.shape)} (bits={bits}) implies K={k}, "
+            f"scales {tuple(scales.shape)} (group_size={group_size})"
+        )
+    if k_x is not None and k_x != k:
+        raise ValueError(f"[quantized_matmul] x last dim {k_x} != K {k}")
+    if scales.dtype != biases.dtype:
+        raise ValueError("[quantized_matmul] scales and biases must share a dtype")
+    return n, k
+
+
+def _qmm_impl(x, w, scales, biases, bias, group_size: int, bits: int, kernel: int) -> torch.Tensor:
+    _require_cuda(x, w, scales, biases, bias)
+    _as_u32_ptr_tensor(w)
+    n, k = _check_shapes(w, scales, biases, group_size, bits, x.shape[-1])
+    if x.dtype != scales.dtype:
+        raise ValueError(
+            f"[quantized_matmul] x ({x.dtype}) and scales ({scales.dtype}) must share a dtype; cast the "
+            "activations like the reference loader casts scales/zeros to bf16 (gbx_lm/utils.py:841-843)"
+        )
+    dt = _dt(x)
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, k)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    w = w.contiguous()
+    scales = scales.contiguous()
+    biases = biases.contiguous()
+    if bias is not None:
+        if bias.dtype != x.dtype or bias.numel() != n:
+            raise ValueError("[quantized_matmul] bias must be [N] in the activation dtype")
+        bias = bias.contiguous()
+    m = x2.shape[0]
+    y = torch.empty((m, n), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        st = torch.cuda.current_stream().cuda_stream
+        rc = _lib.get().gbxq_qmm_ex(
+            x2.data_ptr(), w.data_ptr(), scales.data_ptr(), biases.data_ptr(),
+            bias.data_ptr() if bias is not None else None, y.data_ptr(),
+            m, n, k, bits, group_size, dt, kernel, None, 0, st,
+        )
+    _lib.check(rc, "gbxq_qmm")
+    return y.reshape(*lead, n)
+
+
+@torch.library.custom_op("gbxq::qmm", mutates_args=(), device_types="cuda")
+def _qmm_op(
+    x: torch.Tensor,
+    w: torch.Tensor,
+    scales: torch.Tensor,
+    biases: torch.Tensor,
+    bias: Optional[torch.Tensor],
+    group_size: int,
+    bits: int,
+    kernel: int,
+) -> torch.Tensor:
+    return _qmm_impl(x, w, scales, biases, bias, group_size, bits, kernel)
+
+
+@_qmm_op.register_fake
+def _(x, w, scales, biases, bias, group_size, bits, kernel):
+    return x.new_empty((*x.shape[:-1], w.shape[0]))
+
+
+@torch.library.custom_op("gbxq::dequantize", mutates_args=(), device_types="cuda")
+def _dequantize_op(w: torch.Tensor, scales: torch.Tensor, biases: torch.Tensor, group_size: int, bits: int) -> torch.Tensor:
+    _require_cuda(w, scales, biases)
+    _as_u32_ptr_tensor(w)
+    n, k = _check_shapes(w, scales, biases, group_size, bits, None)
+    dt = _dt(scales)
+    w = w.contiguous()
+    scales = scales.contiguous()
+    biases = biases.contiguous()
+    out = torch.empty((n, k), dtype=scales.dtype, device=w.device)
+    with torch.cuda.device(w.device):
+        st = torch.cuda.current_stream().cuda_stream
+        rc = _lib.get().gbxq_dequantize(w.data_ptr(), scales.data_ptr(), biases.data_ptr(), out.data_ptr(), n, k, bits, group_size, dt, st)
+    _lib.check(rc, "gbxq_dequantize")
+    return out
+
+
+@_dequantize_op.register_fake
+def _(w, scales, biases, group_size, bits):
+    return scales.new_empty((w.shape[0], w.shape[1] * 32 // bits))
+
+
+def quantized_matmul(
+    x: torch.Tensor,
+    w: torch.Tensor,
+    scales: torch.Tensor,
+    biases: torch.Tensor,
+    transpose: bool = True,
+    group_size: int = 64,
+    bits: int = 4,
+    *,
+    bias: Optional[torch.Tensor] = None,
+    kernel: str = "auto",
+) -> torch.Tensor:
+    """Drop-in for `mx.quantized_matmul` as QuantizedLinear calls it (transpose=True only; the
+    transpose=False form is used by the out-of-scope quantized-KV attention, models/base.py:85-93).
+    `bias` fuses QuantizedLinear's `x + bias` (quantized_linear_gba.py:204-205)."""
+    if not transpose:
+        raise NotImplementedError("quantized_matmul(transpose=False) is outside the QuantizedLinear path")
+    return _qmm_op(x, w, scales, biases, bias, int(group_size), int(bits), _KERNELS[kernel])
+
+
+def dequantize(w: torch.Tensor, scales: torch.Tensor, biases: torch.Tensor, group_size: int = 64, bits: int = 4) -> torch.Tensor:
+    """Drop-in for `mx.dequantize` (bit-exact: T(T(scale*q)+bias), T = scales.dtype)."""
+    return _dequantize_op(w, scales, biases, int(group_size), int(bits))
+
+
+def select_kernel(m: int, n: int, k: int, bits: int, group_size: int, dtype: torch.dtype = torch.bfloat16) -> str:
+    rc = _lib.get().gbxq_select_kernel(m, n, k, bits, group_size, _DT[dtype])
+    _lib.check(min(rc, 0), "gbxq_select_kernel")
+    return {1: "generic", 2: "gemv", 3: "gemm"}[rc]
+
+
+def launch_count() -> int:
+    return int(_lib.get().gbxq_launch_count())

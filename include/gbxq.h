@@ -1,0 +1,136 @@
+/*
+ * gbxq.h -- C ABI of libgbxq.so: B200 (sm_100a) group-affine low-bit quantized matmul.
+ *
+ * Drop-in boundary for ONE hot path of GreenBitAI/gbx-lm: the call that
+ * `QuantizedLinear.__call__` makes into the MLX extension module,
+ *
+ *     mx.quantized_matmul(x, qweight, scales=scales, biases=zeros, transpose=True,
+ *                         group_size=gs, bits=b)   gbx_lm/models/quantized_linear_gba.py:195-203
+ *     (+ bias)                                      gbx_lm/models/quantized_linear_gba.py:204-205
+ *     mx.dequantize(w, scales, biases, gs, bits)    gbx_lm/tuner/lora.py:62-68
+ *                                                   gbx_lm/tuner/utils.py:214-220
+ *
+ * The reference has no FFI layer of its own (it is pure Python over the `mlx` wheel); these
+ * entry points are what a ctypes/nanobind binding placed at that seam would call
+ * (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer owned by the caller unless the name ends in `_host`.
+ *     Inputs are never written.  Outputs are fully overwritten.
+ *   - Calls only ENQUEUE work on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *     stream) and return; they never synchronise, never allocate device memory and keep no
+ *     global mutable state, so they are CUDA-graph capturable and thread-safe across streams.
+ *   - Return value: GBXQ_OK (0) or a negative gbxq_status.  Nothing throws.
+ *   - Tensor layout = MLX affine quantisation as emitted by gba2mlx (gbx_lm/gba2mlx.py:47-65,
+ *     gbx_lm/utils.py:828-843):
+ *        qweight  uint32 [N, K*bits/32]  row-major; row n is the LSB-first bitstream of the K codes
+ *                                         of output feature n, cut into little-endian words
+ *        scales   T      [N, K/group_size]
+ *        biases   T      [N, K/group_size]   (the checkpoint's `zeros`: already the ADDITIVE term,
+ *                                            quantized_linear_gba.py:151-155)
+ *        x        T      [M, K]  row-major (M = product of the leading dims)
+ *        y        T      [M, N]  row-major
+ *        bias     T      [N]     optional (Qwen2 q/k/v: gbx_lm/models/qqwen2.py:44-46)
+ *     W[n,k] = scales[n,k/gs] * q[n,k] + biases[n,k/gs];  y = x . W^T (+ bias)
+ *   - T is selected by `dtype` (gbxq_dtype).  bits in {2,3,4,6,8}; group_size in {32,64,128}
+ *     (asserted by the reference at quantized_linear_gba.py:250,272 and utils.py:819-821).
+ */
+#ifndef GBXQ_H_
+#define GBXQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GBXQ_ABI_VERSION 1
+
+typedef enum gbxq_status {
+    GBXQ_OK = 0,
+    GBXQ_EINVAL_BITS = -1,   /* bits not in {2,3,4,6,8} */
+    GBXQ_EINVAL_GROUP = -2,  /* group_size not in {32,64,128} */
+    GBXQ_ESHAPE = -3,        /* M,N,K inconsistent (K % 32, K % group_size, negative, ...) */
+    GBXQ_EDTYPE = -4,        /* unknown dtype code */
+    GBXQ_EALIGN = -5,        /* a pointer is not aligned as required (16 B for x/y/qweight rows) */
+    GBXQ_ENULL = -6,         /* a required pointer is NULL */
+    GBXQ_ECUDA = -7,         /* a CUDA runtime call failed; see gbxq_last_cuda_error() */
+    GBXQ_EWORKSPACE = -8,    /* workspace too small (gbxq_workspace_bytes) */
+    GBXQ_EUNSUPPORTED = -9   /* feature not available for this argument combination */
+} gbxq_status;
+
+typedef enum gbxq_dtype { GBXQ_BF16 = 0, GBXQ_F16 = 1, GBXQ_F32 = 2 } gbxq_dtype;
+
+/* Kernel selection for gbxq_qmm_ex (tests / benchmarks); gbxq_qmm uses GBXQ_KERNEL_AUTO. */
+typedef enum gbxq_kernel {
+    GBXQ_KERNEL_AUTO = 0,
+    GBXQ_KERNEL_GENERIC = 1, /* shape-agnostic warp-per-row kernel (all dtypes)            */
+    GBXQ_KERNEL_GEMV = 2,    /* TMA-bulk ring streaming GEMV, M tiles of 1/2 (bf16)         */
+    GBXQ_KERNEL_GEMM = 3     /* tcgen05/TMEM tensor-core GEMM with in-kernel dequant (bf16) */
+} gbxq_kernel;
+
+/* Library / ABI identification. */
+int gbxq_abi_version(void);
+const char* gbxq_status_string(int status);
+/* Last cudaError_t seen by the calling thread inside libgbxq (0 if none), and its text. */
+int gbxq_last_cuda_error(void);
+const char* gbxq_last_cuda_error_string(void);
+
+/*
+ * y[M,N] = x[M,K] . dequant(qweight)[N,K]^T (+ bias)
+ * Replaces mx.quantized_matmul(..., transpose=True) + the bias add of QuantizedLinear.__call__
+ * (quantized_linear_gba.py:195-205).  Output is rounded once to T; the optional bias is a second,
+ * separately rounded add, as in the reference.  M == 0 or N == 0 is a no-op returning GBXQ_OK.
+ * `workspace` may be NULL when gbxq_workspace_bytes(...) == 0.
+ */
+int gbxq_qmm(const void* x, const uint32_t* qweight, const void* scales, const void* biases,
+             const void* bias /* nullable */, void* y, int64_t M, int64_t N, int64_t K, int bits,
+             int group_size, int dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same, forcing one kernel family (returns GBXQ_EUNSUPPORTED if it cannot serve the arguments). */
+int gbxq_qmm_ex(const void* x, const uint32_t* qweight, const void* scales, const void* biases,
+                const void* bias, void* y, int64_t M, int64_t N, int64_t K, int bits,
+                int group_size, int dtype, int kernel, void* workspace, size_t workspace_bytes,
+                void* stream);
+
+/* Scratch bytes gbxq_qmm may use for these arguments (0 today for every shipped kernel). */
+size_t gbxq_workspace_bytes(int64_t M, int64_t N, int64_t K, int bits, int group_size, int dtype);
+
+/*
+ * w_out[N,K] (T) = T( T(scales * T(q)) + biases )      -- bit-exact with mx.dequantize
+ * Replaces mx.dequantize(w, scales, biases, group_size, bits) (tuner/lora.py:62-68).
+ */
+int gbxq_dequantize(const uint32_t* qweight, const void* scales, const void* biases, void* w_out,
+                    int64_t N, int64_t K, int bits, int group_size, int dtype, void* stream);
+
+/* Which kernel family GBXQ_KERNEL_AUTO picks for these arguments (a gbxq_kernel value, or <0). */
+int gbxq_select_kernel(int64_t M, int64_t N, int64_t K, int bits, int group_size, int dtype);
+
+/* Number of kernel launches libgbxq has enqueued from this process (monotonic; for benches). */
+uint64_t gbxq_launch_count(void);
+
+/*
+ * Tensor-parallel row-parallel epilogue (new work; the reference has no TP -- SURVEY.md 2.2):
+ * one-shot sum all-reduce of a small [count] T vector over peer-mapped buffers on NVLink
+ * (P2P loads/stores, no NCCL call).  Meant for the latency-bound decode messages
+ * (M*hidden*2 bytes: 16 KB .. 1 MB) that follow o_proj / down_proj.
+ *   peer_bufs_dev  : device array of `world` pointers; entry r = rank r's staging buffer of
+ *                    `capacity` elements of T, mapped into THIS process (symmetric memory).
+ *                    The buffer is used as two halves (seq parity), so count <= capacity/2.
+ *   peer_flags_dev : device array of `world` pointers; entry r = rank r's uint32 flag array of
+ *                    world * GBXQ_AR_MAX_CTAS entries, zero-initialised once.
+ *   in  : this rank's partial sums          out: reduced result (rank-order sum, identical on
+ *                                                every rank), may alias `in`
+ *   seq : starts at 1, increases by exactly 1 per call, same on every rank.
+ * Every rank must enqueue the call with the same count/dtype/seq on a stream of its own device.
+ */
+#define GBXQ_AR_MAX_CTAS 32
+int gbxq_allreduce_oneshot(const void* in, void* out, int64_t count, int dtype,
+                           void* const* peer_bufs_dev, uint32_t* const* peer_flags_dev,
+                           int64_t capacity, int rank, int world, uint32_t seq, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GBXQ_H_ */

@@ -1,0 +1,100 @@
+"""CPU tests of the drop-in boundary: libgbxq.so loads without a GPU, exports every symbol that
+include/gbxq.h declares, rejects bad arguments with the documented status codes before touching
+CUDA, and the Python ops refuse CPU tensors (no fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    hdr = open(os.path.join(ROOT, "include", "gbxq.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(gbxq_[a-z_0-9]+)\s*\(", hdr)))
+
+
+def test_header_symbols_exported():
+    from gbx_lm_b200 import _lib
+
+    lib = _lib.get()
+    names = _declared_functions()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/gbxq.h but not exported"
+    assert sorted(_lib.EXPORTS) == names
+    assert lib.gbxq_abi_version() == 1
+
+
+def test_no_torch_types_in_abi():
+    hdr = open(os.path.join(ROOT, "include", "gbxq.h")).read()
+    assert "torch" not in hdr and "at::" not in hdr and "#include <cuda" not in hdr
+
+
+def test_argument_validation_without_gpu():
+    from gbx_lm_b200 import _lib
+
+    lib = _lib.get()
+    p = ctypes.c_void_p(256)  # never dereferenced: validation fails first
+    q = lambda **kw: lib.gbxq_qmm(p, p, p, p, None, p, kw.get("M", 1), kw.get("N", 8), kw.get("K", 64),
+                                  kw.get("bits", 4), kw.get("gs", 64), kw.get("dt", 0), None, 0, None)
+    assert q(bits=5) == -1 and q(bits=1) == -1 and q(bits=16) == -1
+    assert q(gs=16) == -2 and q(gs=256) == -2
+    assert q(K=48) == -3 and q(K=96, gs=64) == -3 and q(M=-1) == -3 and q(K=0) == -3
+    assert q(dt=3) == -4
+    assert q(M=0) == 0 and q(N=0) == 0  # empty problems are no-ops
+    assert lib.gbxq_qmm(None, p, p, p, None, p, 1, 8, 64, 4, 64, 0, None, 0, None) == -6
+    assert lib.gbxq_dequantize(p, p, p, ctypes.c_void_p(8), 8, 64, 4, 64, 0, None) == -5
+    assert lib.gbxq_dequantize(p, p, p, p, 8, 64, 7, 64, 0, None) == -1
+    assert lib.gbxq_workspace_bytes(1, 8, 64, 4, 64, 0) == 0
+    assert b"bits" in lib.gbxq_status_string(-1)
+    assert lib.gbxq_allreduce_oneshot(p, p, 64, 0, p, p, 64, 0, 2, 1, None) == -3  # capacity < 2*count
+    assert lib.gbxq_allreduce_oneshot(p, p, 64, 0, p, p, 256, 2, 2, 1, None) == -3  # rank out of range
+
+
+def test_ops_refuse_cpu_tensors():
+    import gbx_lm_b200 as g
+
+    x = torch.zeros(1, 64, dtype=torch.bfloat16)
+    w = torch.zeros(8, 8, dtype=torch.uint32)
+    s = torch.ones(8, 1, dtype=torch.bfloat16)
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        g.quantized_matmul(x, w, s, s, True, 64, 4)
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        g.dequantize(w, s, s, 64, 4)
+
+
+def test_python_shape_errors_are_value_errors():
+    from gbx_lm_b200 import ops
+
+    w = torch.zeros(8, 8, dtype=torch.uint32)
+    s = torch.ones(8, 1, dtype=torch.bfloat16)
+    with pytest.raises(ValueError):
+        ops._check_shapes(w, s, s, 64, 5, None)
+    with pytest.raises(ValueError):
+        ops._check_shapes(w, s, s, 48, 4, None)
+    with pytest.raises(ValueError):
+        ops._check_shapes(w, torch.ones(8, 2, dtype=torch.bfloat16), torch.ones(8, 2, dtype=torch.bfloat16), 64, 4, None)
+    with pytest.raises(ValueError):
+        ops._check_shapes(w, s, s, 64, 4, 128)
+    assert ops._check_shapes(w, s, s, 64, 4, 64) == (8, 64)
+
+
+def test_quantized_linear_attribute_contract():
+    """Constructor signature, attribute names, shapes and dtypes of quantized_linear_gba.py:36-117."""
+    from gbx_lm_b200 import QuantizedLinear
+
+    for bits in (2, 3, 4, 6, 8):
+        for gs in (32, 64, 128):
+            m = QuantizedLinear(256, 48, bias=(bits == 4), group_size=gs, bits=bits)
+            assert m.qweight.shape == (48, 256 // 32 * bits) and m.qweight.dtype == torch.uint32
+            assert m.scales.shape == (48, 256 // gs) == m.zeros.shape
+            assert m.channel_scale.shape == (1, 1, 256) and m.channel_scale.dtype == torch.float16
+            assert (m.bits, m.group_size, m.input_dims, m.output_dims) == (bits, gs, 256, 48)
+            assert m.weight is m.qweight and m.biases is m.zeros
+            assert (m.bias is not None) == (bits == 4)
+            keys = set(m.state_dict().keys())
+            assert {"qweight", "scales", "zeros", "channel_scale"} <= keys

@@ -1,0 +1,241 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Every call goes through the C ABI
+(libgbxq.so via the torch custom ops); results are checked against the CPU oracle (oracle/), the
+committed golden fixtures, and -- at BASELINE sizes -- size-independent properties."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle as C
+from oracle import mlx_affine as A
+from tests.gpu_util import assert_close_to_truth, bf16_from_bits, bits_from_bf16, layer_to_cuda, u32_to_torch
+
+pytestmark = pytest.mark.gpu
+
+BITS = (2, 3, 4, 6, 8)
+GS = (32, 64, 128)
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "affine_golden.json")))
+
+
+def _ops():
+    import gbx_lm_b200 as g
+
+    return g
+
+
+# ---------------------------------------------------------------------------------- dequantize
+@pytest.mark.parametrize("bits", BITS)
+@pytest.mark.parametrize("gs", GS)
+@pytest.mark.parametrize("dtype", ["bf16", "f16", "f32"])
+def test_dequantize_bit_exact(cuda_device, bits, gs, dtype):
+    g = _ops()
+    N, K = 37, 384
+    L = A.synth_layer(N, K, bits, gs, seed=bits * 100 + gs)
+    s32, z32 = A.bf16_bits_to_f32(L["scales"]), A.bf16_bits_to_f32(L["zeros"])
+    w = u32_to_torch(L["qweight"], cuda_device)
+    if dtype == "bf16":
+        s, z = bf16_from_bits(L["scales"], cuda_device), bf16_from_bits(L["zeros"], cuda_device)
+        ref = A.dequantize(L["qweight"], L["scales"], L["zeros"], gs, bits, "bf16")
+    elif dtype == "f16":
+        s16, z16 = s32.astype(np.float16), z32.astype(np.float16)
+        s, z = torch.from_numpy(s16).to(cuda_device), torch.from_numpy(z16).to(cuda_device)
+        ref = A.dequantize(L["qweight"], s16, z16, gs, bits, "f16")
+    else:
+        s32 = (s32 * np.float32(1.000123)).astype(np.float32)  # use all 24 significand bits
+        s, z = torch.from_numpy(s32).to(cuda_device), torch.from_numpy(z32).to(cuda_device)
+        ref = A.dequantize(L["qweight"], s32, z32, gs, bits, "f32")
+    out = g.dequantize(w, s, z, gs, bits)
+    assert out.shape == (N, K) and out.dtype == s.dtype
+    got = out.float().cpu().numpy()
+    assert (got.view(np.uint32) == ref.astype(np.float32).view(np.uint32)).all()
+
+
+@pytest.mark.parametrize("case", GOLD["dequant"], ids=lambda c: f"b{c['bits']}-{c['dtype']}")
+def test_dequantize_golden(cuda_device, case):
+    g = _ops()
+    tdt = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32}[case["dtype"]]
+    w = u32_to_torch(np.array([case["qweight"]], dtype=np.uint32), cuda_device)
+    s = torch.tensor([[0.0123]], dtype=tdt, device=cuda_device)
+    b = torch.tensor([[-0.771]], dtype=tdt, device=cuda_device)
+    out = g.dequantize(w, s, b, 32, case["bits"]).float().cpu().numpy()
+    assert out.view(np.uint32)[0].tolist() == case["out_f32_hex"]
+
+
+def test_dequantize_full_size_against_c_oracle(cuda_device):
+    """Llama-3-8B k_proj (1024 x 4096, 4-bit gs64) and a 3-bit o_proj slice: checksum of the whole
+    matrix + exact compare, oracle = C restatement (seconds)."""
+    g = _ops()
+    for bits, gs, N, K in ((4, 64, 1024, 4096), (3, 64, 512, 4096), (6, 64, 256, 14336), (2, 128, 512, 3584)):
+        L = A.synth_layer(N, K, bits, gs, seed=bits)
+        ref = C.dequantize(L["qweight"], L["scales"], L["zeros"], gs, bits, "bf16")
+        d = layer_to_cuda(L, cuda_device)
+        out = g.dequantize(d["qweight"], d["scales"], d["zeros"], gs, bits)
+        assert (bits_from_bf16(out) == ref).all()
+
+
+# ---------------------------------------------------------------------------------- quantized matmul
+def _run_case(g, dev, kernel, bits, gs, M, N, K, seed, with_bias=False):
+    L = A.synth_layer(N, K, bits, gs, seed=seed, with_bias=with_bias)
+    x = A.synth_x(M, K, seed=seed + 1)
+    d = layer_to_cuda(L, dev)
+    y = g.quantized_matmul(bf16_from_bits(x, dev), d["qweight"], d["scales"], d["zeros"], True, gs, bits,
+                           bias=d.get("bias"), kernel=kernel)
+    ref = A.quantized_matmul(x, L["qweight"], L["scales"], L["zeros"], gs, bits, "bf16", "f64", bias=L.get("bias"))
+    assert y.shape == (M, N) and y.dtype == torch.bfloat16
+    return assert_close_to_truth(y, ref, f"{kernel} b{bits} g{gs} M{M} N{N} K{K}")
+
+
+@pytest.mark.parametrize("kernel", ["generic", "gemv"])
+@pytest.mark.parametrize("bits", BITS)
+@pytest.mark.parametrize("gs", GS)
+def test_qmm_vs_oracle_small(cuda_device, kernel, bits, gs):
+    g = _ops()
+    for M in (1, 2, 3):
+        _run_case(g, cuda_device, kernel, bits, gs, M, 70, 1024, seed=bits * 31 + gs + M)
+
+
+@pytest.mark.parametrize("bits", BITS)
+def test_qmm_gemv_model_shapes(cuda_device, bits):
+    """Shapes of the configs: ragged K (14336 = 14 pieces, 3584 = TP shard of 28672),
+    N smaller / not a multiple of the grid, M = 1 and 2."""
+    g = _ops()
+    for (N, K) in ((300, 4096), (96, 14336), (150, 3584), (1, 2048), (147, 8192), (149, 3072)):
+        for M in (1, 2):
+            if bits == 3 and K % 128:
+                continue
+            _run_case(g, cuda_device, "gemv", bits, 64, M, N, K, seed=N + K + bits)
+
+
+def test_qmm_auto_dispatch_and_bias(cuda_device):
+    g = _ops()
+    for M in (1, 2, 4, 5, 16):
+        _run_case(g, cuda_device, "auto", 4, 64, M, 512, 2048, seed=77 + M, with_bias=True)
+    _run_case(g, cuda_device, "gemv", 2, 128, 1, 256, 2048, seed=5, with_bias=True)
+    _run_case(g, cuda_device, "generic", 6, 32, 3, 33, 96 * 4, seed=6, with_bias=True)
+
+
+@pytest.mark.parametrize("case", GOLD["qmm"], ids=lambda c: f"b{c['bits']}-g{c['group_size']}")
+def test_qmm_golden_fixtures(cuda_device, case):
+    """Committed fixtures: GPU output within one bf16 ulp of the fp64-truth rounded to bf16."""
+    g = _ops()
+    w = u32_to_torch(np.array(case["qweight"], dtype=np.uint32), cuda_device)
+    s = bf16_from_bits(np.array(case["scales_bf16"], dtype=np.uint16), cuda_device)
+    z = bf16_from_bits(np.array(case["zeros_bf16"], dtype=np.uint16), cuda_device)
+    x = bf16_from_bits(np.array(case["x_bf16"], dtype=np.uint16), cuda_device)
+    gold = A.bf16_bits_to_f32(np.array(case["y_bf16"], dtype=np.uint16))
+    for kernel in ("generic", "gemv"):
+        y = g.quantized_matmul(x, w, s, z, True, case["group_size"], case["bits"], kernel=kernel).float().cpu().numpy()
+        ulp = np.maximum(np.abs(gold) * 2.0 ** -7, np.abs(gold).max() * 2.0 ** -9)
+        assert (np.abs(y - gold) <= ulp).all(), kernel
+
+
+def test_qmm_generic_f16_f32(cuda_device):
+    g = _ops()
+    N, K, M, bits, gs = 40, 512, 3, 4, 64
+    L = A.synth_layer(N, K, bits, gs, seed=8)
+    x32 = A.bf16_bits_to_f32(A.synth_x(M, K, seed=9))
+    s32, z32 = A.bf16_bits_to_f32(L["scales"]), A.bf16_bits_to_f32(L["zeros"])
+    w = u32_to_torch(L["qweight"], cuda_device)
+    for tdt, name in ((torch.float16, "f16"), (torch.float32, "f32")):
+        npdt = np.float16 if name == "f16" else np.float32
+        y = g.quantized_matmul(torch.from_numpy(x32.astype(npdt)).to(cuda_device), w,
+                               torch.from_numpy(s32.astype(npdt)).to(cuda_device),
+                               torch.from_numpy(z32.astype(npdt)).to(cuda_device), True, gs, bits)
+        ref = A.quantized_matmul(x32.astype(npdt), L["qweight"], s32.astype(npdt), z32.astype(npdt), gs, bits, name, "f64")
+        assert y.dtype == tdt
+        tol = 2.0 ** -10 if name == "f16" else 1e-5
+        assert np.abs(y.float().cpu().numpy() - ref).max() <= tol * np.abs(ref).max()
+
+
+def test_edge_cases(cuda_device):
+    g = _ops()
+    L = A.synth_layer(16, 64, 4, 64, seed=1)
+    d = layer_to_cuda(L, cuda_device)
+    # empty batch
+    y = g.quantized_matmul(torch.zeros((0, 64), dtype=torch.bfloat16, device=cuda_device), d["qweight"], d["scales"], d["zeros"], True, 64, 4)
+    assert y.shape == (0, 16)
+    # leading dims [B, L, K] and a non-contiguous x
+    x = bf16_from_bits(A.synth_x(6, 128, seed=2), cuda_device)[:, ::2].reshape(2, 3, 64)
+    y = g.quantized_matmul(x, d["qweight"], d["scales"], d["zeros"], True, 64, 4)
+    xb = bits_from_bf16(x.reshape(6, 64))
+    ref = A.quantized_matmul(xb, L["qweight"], L["scales"], L["zeros"], 64, 4, "bf16", "f64")
+    assert y.shape == (2, 3, 16)
+    assert_close_to_truth(y.reshape(6, 16), ref, "3-D non-contiguous x")
+    # int32-typed qweight (same bits) is accepted
+    y2 = g.quantized_matmul(x, d["qweight"].view(torch.int32), d["scales"], d["zeros"], True, 64, 4)
+    assert torch.equal(y, y2)
+    # K = 32 (one word-block) with the smallest group
+    _run_case(g, cuda_device, "auto", 8, 32, 1, 3, 32, seed=3)
+    # errors: ValueError like MLX
+    with pytest.raises(ValueError):
+        g.quantized_matmul(x, d["qweight"], d["scales"], d["zeros"], True, 64, 5)
+    with pytest.raises(ValueError):
+        g.quantized_matmul(x, d["qweight"], d["scales"], d["zeros"], True, 32, 4)
+    with pytest.raises(ValueError):
+        g.quantized_matmul(x.float(), d["qweight"], d["scales"], d["zeros"], True, 64, 4)
+    with pytest.raises(ValueError):
+        g.quantized_matmul(x, d["qweight"].float(), d["scales"], d["zeros"], True, 64, 4)
+    with pytest.raises(NotImplementedError):
+        g.quantized_matmul(x, d["qweight"], d["scales"], d["zeros"], False, 64, 4)
+    from gbx_lm_b200 import ops
+
+    with pytest.raises(ValueError):  # forced fast kernel on unsupported arguments surfaces, never falls back silently
+        ops.quantized_matmul(torch.zeros((1, 32), dtype=torch.float16, device=cuda_device),
+                             torch.zeros((4, 4), dtype=torch.uint32, device=cuda_device),
+                             torch.ones((4, 1), dtype=torch.float16, device=cuda_device),
+                             torch.ones((4, 1), dtype=torch.bfloat16, device=cuda_device), True, 32, 4)
+
+
+# ---------------------------------------------------------------------------------- full-size properties
+def test_full_size_8b_gate_proj_properties(cuda_device):
+    """Llama-3-8B gate_proj (14336 x 4096, 4-bit gs64) at M=1/2: (a) sampled rows vs oracle,
+    (b) consistency with x . dequantize()^T, (c) split-K additivity (the row-parallel TP identity)."""
+    g = _ops()
+    N, K, bits, gs = 14336, 4096, 4, 64
+    P = __import__("gbx_lm_b200.packing", fromlist=["x"])
+    L = P.synth_layer(N, K, bits, gs, seed=11)
+    qw, s, z = L["qweight"].to(cuda_device), L["scales"].to(cuda_device), L["zeros"].to(cuda_device)
+    x = torch.randn((2, K), generator=torch.Generator().manual_seed(12)).to(torch.bfloat16).to(cuda_device)
+    y = g.quantized_matmul(x, qw, s, z, True, gs, bits, kernel="gemv")
+    # (a) 64 sampled rows against the oracle
+    rows = np.random.default_rng(0).choice(N, 64, replace=False)
+    ref = A.quantized_matmul(bits_from_bf16(x), L["qweight"][rows].view(torch.int32).numpy().view(np.uint32),
+                             bits_from_bf16(L["scales"][rows]), bits_from_bf16(L["zeros"][rows]), gs, bits, "bf16", "f64")
+    assert_close_to_truth(y[:, torch.from_numpy(rows).to(cuda_device)], ref, "sampled rows")
+    # (b) matmul against the GPU-dequantised matrix in fp32
+    W = g.dequantize(qw, s, z, gs, bits).float()
+    y_deq = x.float() @ W.t()
+    assert (y.float() - y_deq).abs().max() <= 2.0 ** -6 * y_deq.abs().max()
+    # (c) split-K additivity: y(W) == y(W[:, :K/2]) + y(W[:, K/2:]) up to bf16 rounding of the halves
+    h = K // 2
+    wh = h * bits // 32
+    y0 = g.quantized_matmul(x[:, :h].contiguous(), qw[:, :wh].contiguous(), s[:, : h // gs].contiguous(), z[:, : h // gs].contiguous(), True, gs, bits)
+    y1 = g.quantized_matmul(x[:, h:].contiguous(), qw[:, wh:].contiguous(), s[:, h // gs :].contiguous(), z[:, h // gs :].contiguous(), True, gs, bits)
+    assert (y.float() - (y0.float() + y1.float())).abs().max() <= 2.0 ** -6 * y.float().abs().max()
+    # M=1 equals the first row of the M=2 call (rows of x are independent)
+    y_m1 = g.quantized_matmul(x[:1], qw, s, z, True, gs, bits, kernel="gemv")
+    assert torch.equal(y_m1, y[:1])
+
+
+def test_cuda_graph_capture(cuda_device):
+    g = _ops()
+    L = A.synth_layer(256, 1024, 4, 64, seed=21)
+    d = layer_to_cuda(L, cuda_device)
+    x = bf16_from_bits(A.synth_x(1, 1024, seed=22), cuda_device)
+    eager = g.quantized_matmul(x, d["qweight"], d["scales"], d["zeros"], True, 64, 4)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            g.quantized_matmul(x, d["qweight"], d["scales"], d["zeros"], True, 64, 4)
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = g.quantized_matmul(x, d["qweight"], d["scales"], d["zeros"], True, 64, 4)
+    x.copy_(bf16_from_bits(A.synth_x(1, 1024, seed=23), cuda_device))
+    graph.replay()
+    torch.cuda.synchronize()
+    ref = g.quantized_matmul(x, d["qweight"], d["scales"], d["zeros"], True, 64, 4)
+    assert torch.equal(out, ref) and not torch.equal(out, eager)
