@@ -1,27 +1,31 @@
 // gbxq_gemv.cu -- decode GEMV / skinny matmul (M tiles of 1 or 2 tokens) for bf16 activations.
 //
 // Hot path of gbx-lm decode: QuantizedLinear.__call__ -> mx.quantized_matmul(transpose=True)
-// (gbx_lm/models/quantized_linear_gba.py:195-203) with M = batch (1..) rows of x.
+// (gbx_lm/models/quantized_linear_gba.py:195-203) with M = batch rows of x.
 //
-// HBM-bound by design: every packed weight byte is read from HBM exactly once per M tile.
+// HBM-bound by design: every packed weight byte is read from HBM exactly once per M tile and the
+// only shared-memory traffic of the main loop is that same byte stream (one TMA write + one LDS).
 //
-//   * qweight is row-major [N, K*bits/32] so the packed rows owned by one CTA form ONE
-//     contiguous byte range.  That range is cut into "pieces" (one warp sweep: 32 lanes x
-//     16 B, or 32 x 48 B for the 3/6-bit packings) and streamed through a 4-stage shared-memory
-//     ring by the TMA engine: one `cp.async.bulk` (SASS UBLKCP) of up to 16/24 KB per stage,
-//     completion counted in bytes on an mbarrier (full/empty barrier pair per stage, a dedicated
-//     producer warp).  64-96 KB in flight per SM, independent of occupancy.
-//   * 16 consumer warps read the ring with conflict-free LDS.128 and unpack in registers:
-//     (w >> s) & mask | 0x4300 builds two bf16 values (128 + q) per LOP3; FHFMA.BF16
-//     (fma.rn.f32.bf16) multiplies them with packed bf16 activations into fp32 accumulators, so
-//     there is no int->float conversion and no activation unpacking.  3- and 6-bit codes that
-//     straddle a 32-bit word are fetched with one funnel shift.
+//   * qweight is row-major [N, K*bits/32]: the packed rows owned by one CTA are ONE contiguous byte
+//     range, and so are their scales and biases.  A dedicated producer warp streams them through a
+//     4-stage shared-memory ring with the TMA engine: per stage one `cp.async.bulk` (SASS UBLKCP) of
+//     up to 32 KB of whole rows plus one each for the rows' scales and biases, completion counted in
+//     bytes on an mbarrier (full/empty pair per stage).  ~128 KB in flight per SM, independent of
+//     occupancy.  Rows are balanced over the grid at single-row granularity.
+//   * The activations are STATIONARY IN REGISTERS: the 16 consumer warps form a (chunk-column x
+//     row-group) grid; a warp owns one 32-lane x 16 B (48 B for 3/6-bit) column of every row and
+//     keeps the matching slice of x, pre-permuted into packed bf16 pairs, in registers for the whole
+//     kernel.  Per row a lane issues one conflict-free LDS.128 (three for 3/6-bit) and unpacks in
+//     registers: (w >> s) & mask | 0x4300 builds two bf16 values (128 + q) per LOP3, FHFMA.BF16
+//     (fma.rn.f32.bf16) multiplies them with the packed activations into fp32 accumulators: no
+//     int->float conversion, no activation unpacking.  3-/6-bit codes that straddle a 32-bit word
+//     are fetched with one funnel shift.
 //   * group affine:  y += scale * sum(x*(q+OFF)) + (bias - OFF*scale) * sum(x) per (row, group
-//     fragment); sum(x) per fragment is precomputed once per CTA.
-//   * rows are balanced across the grid at single-row granularity (<= 1 row of imbalance);
-//     lanes reduce with warp shuffles only when a warp leaves a row, partial rows shared by two
-//     warps meet in shared-memory atomics, the epilogue rounds once to bf16 (+ optional bias as a
-//     second rounded add) and stores coalesced.
+//     fragment); sum(x) per fragment is a register constant.
+//   * per stage a warp reduces its <=4 row partials with a transposing shuffle butterfly
+//     (6 shuffles for 4 rows), every chunk column owns a shared-memory slot per row (no atomics: results are
+//     bitwise reproducible), and the epilogue sums the columns in fixed order, rounds
+//     once to bf16 (+ optional bias as a second rounded add) and stores coalesced.
 #include "gbxq_common.cuh"
 
 namespace gbxq {
@@ -31,45 +35,41 @@ namespace {
 constexpr int kConsumerWarps = 16;
 constexpr int kThreads = (kConsumerWarps + 1) * 32;
 constexpr int kStages = 4;
+constexpr int kRowsPerWarp = 4;               // R: rows a warp handles per ring stage
+constexpr int kStageWBytes = 32 * 1024;       // packed-weight bytes per ring stage (upper bound)
 constexpr int kMaxRowsPerCta = 2048;
-constexpr uint32_t kMagic = 0x43004300u;  // bf16x2 (128.0, 128.0): OR-ing a code < 128 into the mantissa gives 128+q
+constexpr uint32_t kMagic = 0x43004300u;      // bf16x2 (128, 128): OR-ing a code < 128 into the mantissa gives 128+q
 
 template <int BITS> struct Fmt;
 // UB: bytes per lane-unit, CPU: codes per lane-unit, ATOMS: processing atoms per unit,
-// XPA: 16-byte x vectors per atom, OFF: additive offset carried by the unpacked codes.
-template <> struct Fmt<2> { static constexpr int UB = 16, CPU = 64, ATOMS = 4, XPA = 2, OFF = 128, PPS = 32; };
-template <> struct Fmt<3> { static constexpr int UB = 48, CPU = 128, ATOMS = 4, XPA = 4, OFF = 128, PPS = 16; };
-template <> struct Fmt<4> { static constexpr int UB = 16, CPU = 32, ATOMS = 4, XPA = 1, OFF = 128, PPS = 32; };
-template <> struct Fmt<6> { static constexpr int UB = 48, CPU = 64, ATOMS = 4, XPA = 2, OFF = 128, PPS = 16; };
-template <> struct Fmt<8> { static constexpr int UB = 16, CPU = 16, ATOMS = 2, XPA = 1, OFF = 256, PPS = 32; };
+// OFF: additive offset carried by the unpacked codes.
+template <> struct Fmt<2> { static constexpr int UB = 16, CPU = 64, ATOMS = 4, OFF = 128; };
+template <> struct Fmt<3> { static constexpr int UB = 48, CPU = 128, ATOMS = 4, OFF = 128; };
+template <> struct Fmt<4> { static constexpr int UB = 16, CPU = 32, ATOMS = 4, OFF = 128; };
+template <> struct Fmt<6> { static constexpr int UB = 48, CPU = 64, ATOMS = 4, OFF = 128; };
+template <> struct Fmt<8> { static constexpr int UB = 16, CPU = 16, ATOMS = 2, OFF = 256; };
 
-// position of code i (0 <= i < CPU) inside the lane-unit's permuted activation block
-template <int BITS> __device__ __forceinline__ int xpos(int i) {
-    if constexpr (BITS == 4) {  // word j: LOP3 on (w >> 4t) pairs nibble t with nibble t+4
-        const int j = i >> 3, t = i & 3, h = (i >> 2) & 1;
-        return 2 * (4 * j + t) + h;
-    } else if constexpr (BITS == 2) {  // pairs field t with field t+8
-        const int j = i >> 4, t = i & 7, h = (i >> 3) & 1;
-        return 2 * (8 * j + t) + h;
-    } else if constexpr (BITS == 8) {  // pairs byte t with byte t+2
-        const int j = i >> 2, t = i & 1, h = (i >> 1) & 1;
-        return 2 * (2 * j + t) + h;
-    } else {
-        return i;  // 3/6-bit: natural order
-    }
+// Pair p of a lane-unit multiplies codes (pair_a, pair_b): the two codes one LOP3 extracts together.
+template <int BITS> __host__ __device__ constexpr int pair_a(int p) {
+    if (BITS == 4) return 8 * (p >> 2) + (p & 3);        // word j = p/4: nibble t with nibble t+4
+    if (BITS == 2) return 16 * (p >> 3) + (p & 7);       // word j = p/8: field t with field t+8
+    if (BITS == 8) return 4 * (p >> 1) + (p & 1);        // word j = p/2: byte t with byte t+2
+    return 2 * p;                                        // 3/6-bit: natural order
+}
+template <int BITS> __host__ __device__ constexpr int pair_b(int p) {
+    if (BITS == 4) return pair_a<4>(p) + 4;
+    if (BITS == 2) return pair_a<2>(p) + 8;
+    if (BITS == 8) return pair_a<8>(p) + 2;
+    return 2 * p + 1;
 }
 
 __device__ __forceinline__ uint16_t lo16(uint32_t v) { return (uint16_t)(v & 0xffffu); }
 __device__ __forceinline__ uint16_t hi16(uint32_t v) { return (uint16_t)(v >> 16); }
-__device__ __forceinline__ uint32_t comp(const uint4& v, int i) {
-    return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
-}
 
 // One atom: accumulate sum_k x[k] * (q[k] + OFF) for the atom's codes into acc[m].
-// `w` points at the unit's words in registers, `a` is the atom index, xv[m][XPA] the atom's x vectors.
-template <int BITS, int MT>
-__device__ __forceinline__ void atom_dot(const uint32_t* w, int a, const uint4 (&xv)[MT][Fmt<BITS>::XPA],
-                                         float (&acc)[MT]) {
+// `w` = the unit's words, `a` = atom index, xr[m] = the unit's activation pairs (pair order above).
+template <int BITS, int MT, int NP>
+__device__ __forceinline__ void atom_dot(const uint32_t* w, int a, const uint32_t (&xr)[MT][NP], float (&acc)[MT]) {
     if constexpr (BITS == 4) {
         const uint32_t word = w[a];
 #pragma unroll
@@ -77,9 +77,9 @@ __device__ __forceinline__ void atom_dot(const uint32_t* w, int a, const uint4 (
             const uint32_t v = lop3_and_or(word >> (4 * t), 0x000f000fu, kMagic);
 #pragma unroll
             for (int m = 0; m < MT; m++) {
-                const uint32_t xr = comp(xv[m][0], t);
-                acc[m] = fma_bf16_f32(lo16(v), lo16(xr), acc[m]);
-                acc[m] = fma_bf16_f32(hi16(v), hi16(xr), acc[m]);
+                const uint32_t x2 = xr[m][4 * a + t];
+                acc[m] = fma_bf16_f32(lo16(v), lo16(x2), acc[m]);
+                acc[m] = fma_bf16_f32(hi16(v), hi16(x2), acc[m]);
             }
         }
     } else if constexpr (BITS == 2) {
@@ -89,9 +89,9 @@ __device__ __forceinline__ void atom_dot(const uint32_t* w, int a, const uint4 (
             const uint32_t v = lop3_and_or(word >> (2 * t), 0x00030003u, kMagic);
 #pragma unroll
             for (int m = 0; m < MT; m++) {
-                const uint32_t xr = comp(xv[m][t >> 2], t & 3);
-                acc[m] = fma_bf16_f32(lo16(v), lo16(xr), acc[m]);
-                acc[m] = fma_bf16_f32(hi16(v), hi16(xr), acc[m]);
+                const uint32_t x2 = xr[m][8 * a + t];
+                acc[m] = fma_bf16_f32(lo16(v), lo16(x2), acc[m]);
+                acc[m] = fma_bf16_f32(hi16(v), hi16(x2), acc[m]);
             }
         }
     } else if constexpr (BITS == 8) {
@@ -106,11 +106,11 @@ __device__ __forceinline__ void atom_dot(const uint32_t* w, int a, const uint4 (
                 const uint32_t v2 = lop3_and_or(sh, 0x00800080u, kMagic);
 #pragma unroll
                 for (int m = 0; m < MT; m++) {
-                    const uint32_t xr = comp(xv[m][0], 2 * j + t);
-                    acc[m] = fma_bf16_f32(lo16(v1), lo16(xr), acc[m]);
-                    acc[m] = fma_bf16_f32(hi16(v1), hi16(xr), acc[m]);
-                    acc[m] = fma_bf16_f32(lo16(v2), lo16(xr), acc[m]);
-                    acc[m] = fma_bf16_f32(hi16(v2), hi16(xr), acc[m]);
+                    const uint32_t x2 = xr[m][4 * a + 2 * j + t];
+                    acc[m] = fma_bf16_f32(lo16(v1), lo16(x2), acc[m]);
+                    acc[m] = fma_bf16_f32(hi16(v1), hi16(x2), acc[m]);
+                    acc[m] = fma_bf16_f32(lo16(v2), lo16(x2), acc[m]);
+                    acc[m] = fma_bf16_f32(hi16(v2), hi16(x2), acc[m]);
                 }
             }
         }
@@ -129,8 +129,8 @@ __device__ __forceinline__ void atom_dot(const uint32_t* w, int a, const uint4 (
             const uint32_t v = lop3_and_or(sh, MASK, 0x4300u);
 #pragma unroll
             for (int m = 0; m < MT; m++) {
-                const uint32_t xr = comp(xv[m][t >> 3], (t & 7) >> 1);
-                acc[m] = fma_bf16_f32(lo16(v), (t & 1) ? hi16(xr) : lo16(xr), acc[m]);
+                const uint32_t x2 = xr[m][(a * NC + t) >> 1];
+                acc[m] = fma_bf16_f32(lo16(v), (t & 1) ? hi16(x2) : lo16(x2), acc[m]);
             }
         }
     }
@@ -144,58 +144,72 @@ struct GemvParams {
     const __nv_bfloat16* bias;
     __nv_bfloat16* y;
     int64_t N, K;
-    int M;       // rows of x in this launch (<= MT)
-    int gs_shift;  // log2(group_size)
-    int G;         // K / group_size
+    int M;          // rows of x in this launch (<= MT)
+    int gs_shift;   // log2(group_size)
+    int G;          // K / group_size
     uint32_t row_bytes;
-    int nch;       // pieces per row
-    uint32_t nch_mul;  // floor(2^32 / nch) + 1 (exact division of piece indices by nch; unused when nch == 1)
-    uint32_t xs_stride;  // bytes between the permuted x blocks of consecutive tokens
-    int n_xsum;          // K / SBC
+    int nch;        // 32-lane chunk columns per row
+    int cw, rg;     // warp grid: cw chunk columns x rg row groups (cw * rg <= 16)
+    int tr;         // rows per ring stage (<= rg * kRowsPerWarp)
+    uint32_t slot_bytes;  // ring slot size
+    uint32_t sb_off;      // offset of the scales inside a slot (biases follow at sb_off + tr*G*2)
 };
 
-template <int BITS, int NSB, int MT>
+// Transposing butterfly: R per-lane partial sums -> lane 8*i of the warp holds the full sum of row i
+// (valid where (lane & 7) == 0, row index = lane >> 3).
+template <int R> __device__ __forceinline__ float reduce_rows(const float (&v)[R], int lane) {
+    static_assert(R == 4, "kRowsPerWarp");
+    const bool h16 = lane & 16, h8 = lane & 8;
+    float k0 = h16 ? v[2] : v[0], k1 = h16 ? v[3] : v[1];
+    const float s0 = h16 ? v[0] : v[2], s1 = h16 ? v[1] : v[3];
+    k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+    k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+    float b = h8 ? k1 : k0;
+    const float snd = h8 ? k0 : k1;
+    b += __shfl_xor_sync(0xffffffffu, snd, 8);
+    b += __shfl_xor_sync(0xffffffffu, b, 4);
+    b += __shfl_xor_sync(0xffffffffu, b, 2);
+    b += __shfl_xor_sync(0xffffffffu, b, 1);
+    return b;
+}
+
+template <int BITS, int NSB, int MT, int CPW, bool SB_TMA>
 __global__ void __launch_bounds__(kThreads, 1) gemv_kernel(const GemvParams p) {
     using F = Fmt<BITS>;
-    constexpr int UB = F::UB, CPU = F::CPU, PPS = F::PPS;
-    constexpr int PIECE_B = 32 * UB;            // bytes of one full piece
-    constexpr int STAGE_B = PPS * PIECE_B;      // ring slot size
-    constexpr int PPW = PPS / kConsumerWarps;   // pieces per consumer warp per stage
-    constexpr int VPU = CPU / 8;                // x vectors per unit
-    constexpr int SBC = CPU / NSB;              // codes per scale fragment (== min(CPU, group_size))
-    constexpr int APS = F::ATOMS / NSB;         // atoms per fragment
-    constexpr int NW = UB / 4;                  // words per unit
-    static_assert(PPW >= 1, "stage too small");
+    constexpr int UB = F::UB, CPU = F::CPU;
+    constexpr int CHUNK_B = 32 * UB;         // bytes one warp sweep covers in a row
+    constexpr int SBC = CPU / NSB;           // codes per scale fragment (== min(CPU, group_size))
+    constexpr int APS = F::ATOMS / NSB;      // atoms per fragment
+    constexpr int NW = UB / 4;               // words per unit
+    constexpr int NP = CPU / 2;              // activation pairs per unit
+    constexpr int NV = CPU / 8;              // 16-byte activation vectors per unit
+    constexpr int R = kRowsPerWarp;
 
     extern __shared__ __align__(1024) uint8_t smem[];
-    // layout: [ring kStages*STAGE_B][x MT*xs_stride][xsum MT*n_xsum f32][ysum rows*MT f32][barriers]
+    // layout: [ring kStages * slot_bytes][barriers][ypart rows*cw*MT f32: one slot per (row, chunk column, token)]
     uint8_t* ring = smem;
-    uint8_t* xs = ring + kStages * STAGE_B;
-    float* xsum = reinterpret_cast<float*>(xs + (size_t)MT * p.xs_stride);
-    float* ysum = xsum + (((size_t)MT * p.n_xsum + 3) & ~(size_t)3);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + (size_t)kStages * p.slot_bytes);
+    uint64_t* empty_bar = full_bar + kStages;
+    float* ysum = reinterpret_cast<float*>(empty_bar + kStages);
 
     const int grid = gridDim.x;
     const int64_t r0 = ((int64_t)blockIdx.x * p.N) / grid;
     const int64_t r1 = ((int64_t)(blockIdx.x + 1) * p.N) / grid;
     const int rows = (int)(r1 - r0);
     if (rows <= 0) return;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ysum + (size_t)kMaxRowsPerCta * MT);
-    uint64_t* empty_bar = full_bar + kStages;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int nch = p.nch;
-    const uint32_t nch_mul = p.nch_mul;
-    // piece index -> CTA-local row (exact for piece * nch < 2^32)
-    auto row_of = [&](int piece) -> int { return nch == 1 ? piece : (int)__umulhi((uint32_t)piece, nch_mul); };
-    const int npieces = rows * nch;
-    const int nstage_iters = (npieces + PPS - 1) / PPS;
+    // balanced stage sizing: ns stages of `spr` (<= tr) rows
+    const int ns = (rows + p.tr - 1) / p.tr;
+    const int spr = (rows + ns - 1) / ns;
+    const int active_warps = p.cw * p.rg;
 
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; s++) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], kConsumerWarps);
+            mbar_init(&empty_bar[s], active_warps);
         }
         fence_mbar_init();
     }
@@ -204,252 +218,278 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_kernel(const GemvParams p) {
     if (warp == kConsumerWarps) {
         // ===================== producer warp: one elected lane drives the TMA engine =====================
         if (lane == 0) {
-            for (int it = 0; it < nstage_iters; it++) {
+            const uint8_t* wsrc = p.w + (uint64_t)r0 * p.row_bytes;
+            const uint32_t g2 = (uint32_t)p.G * 2u;  // bytes of one row of scales (or biases)
+            for (int it = 0; it < ns; it++) {
                 const int s = it % kStages;
                 const uint32_t phase = (uint32_t)(it / kStages) & 1u;
                 mbar_wait(&empty_bar[s], phase ^ 1u);
-                const int pa = it * PPS;
-                int pb = pa + PPS;
-                if (pb > npieces) pb = npieces;
-                // byte offset of piece q (relative to row r0): (q / nch) * row_bytes + (q % nch) * PIECE_B
-                const int ra = row_of(pa), ca = pa - ra * nch;
-                const int rb = row_of(pb - 1), cb = (pb - 1) - rb * nch;
-                const uint64_t off_a = (uint64_t)ra * p.row_bytes + (uint64_t)ca * PIECE_B;
-                uint32_t last_sz = p.row_bytes - (uint32_t)cb * PIECE_B;
-                if (last_sz > (uint32_t)PIECE_B) last_sz = PIECE_B;
-                const uint64_t off_b = (uint64_t)rb * p.row_bytes + (uint64_t)cb * PIECE_B + last_sz;
-                const uint32_t bytes = (uint32_t)(off_b - off_a);
-                mbar_arrive_expect_tx(&full_bar[s], bytes);
-                bulk_g2s(ring + (size_t)s * STAGE_B, p.w + (uint64_t)r0 * p.row_bytes + off_a, bytes, &full_bar[s]);
+                const int ra = it * spr;
+                int nr = rows - ra;
+                if (nr > spr) nr = spr;
+                const uint32_t wbytes = (uint32_t)nr * p.row_bytes;
+                uint8_t* slot = ring + (size_t)s * p.slot_bytes;
+                if constexpr (SB_TMA) {
+                    const uint32_t sbytes = (uint32_t)nr * g2;
+                    mbar_arrive_expect_tx(&full_bar[s], wbytes + 2u * sbytes);
+                    bulk_g2s(slot, wsrc + (uint64_t)ra * p.row_bytes, wbytes, &full_bar[s]);
+                    const uint64_t soff = (uint64_t)(r0 + ra) * g2;
+                    bulk_g2s(slot + p.sb_off, reinterpret_cast<const uint8_t*>(p.scales) + soff, sbytes, &full_bar[s]);
+                    bulk_g2s(slot + p.sb_off + (uint32_t)p.tr * g2, reinterpret_cast<const uint8_t*>(p.biases) + soff,
+                             sbytes, &full_bar[s]);
+                } else {
+                    mbar_arrive_expect_tx(&full_bar[s], wbytes);
+                    bulk_g2s(slot, wsrc + (uint64_t)ra * p.row_bytes, wbytes, &full_bar[s]);
+                }
             }
         }
-    } else {
+    } else if (warp < active_warps) {
         // ===================== consumer warps =====================
-        const int ctid = threadIdx.x;  // 0 .. 511
-        constexpr int CT = kConsumerWarps * 32;
-        // ---- prologue (overlaps the first TMA stages): stage x permuted, sum(x) per fragment, zero ysum
-        for (int i = ctid; i < rows * MT; i += CT) ysum[i] = 0.f;
-        {
-            const int K = (int)p.K;
-            uint16_t* xs16 = reinterpret_cast<uint16_t*>(xs);
-            const uint16_t* xg = reinterpret_cast<const uint16_t*>(p.x);
+        const int cwi = warp % p.cw;  // chunk column
+        const int rgi = warp / p.cw;  // row group
+        // ---- stationary activations: this lane's slice of x for each of its chunk columns, as packed
+        //      bf16 pairs in LOP3 pairing order; sum(x) per scale fragment; group index of the unit
+        uint32_t xr[CPW][MT][NP];
+        float xsum[CPW][MT][NSB];
+        int gidx[CPW];
+        bool live[CPW];
+#pragma unroll
+        for (int j = 0; j < CPW; j++) {
+            const int c = cwi + j * p.cw;
+            const uint32_t ubyte = (uint32_t)c * CHUNK_B + (uint32_t)lane * UB;
+            live[j] = (c < p.nch) && (ubyte < p.row_bytes);
+            const int k0 = (c * 32 + lane) * CPU;
+            gidx[j] = k0 >> p.gs_shift;
+#pragma unroll
             for (int m = 0; m < MT; m++) {
-                const bool live = m < p.M;
-                for (int k = ctid; k < K; k += CT) {
-                    const int u = k / CPU, i = k - u * CPU;
-                    const int c = u >> 5, l = u & 31;
-                    const int pos = xpos<BITS>(i);
-                    const int dst = (((c * VPU + (pos >> 3)) * 32 + l) << 3) + (pos & 7);
-                    xs16[(size_t)m * (p.xs_stride >> 1) + dst] = live ? xg[(size_t)m * K + k] : (uint16_t)0;
+                uint4 nat[NV];
+                const bool ld = live[j] && (m < p.M);
+                const uint4* src = reinterpret_cast<const uint4*>(p.x + (size_t)m * p.K + k0);
+#pragma unroll
+                for (int v = 0; v < NV; v++) nat[v] = ld ? __ldg(src + v) : make_uint4(0u, 0u, 0u, 0u);
+                uint32_t n32[NP];  // n32[i] = codes (2i, 2i+1) in natural order
+#pragma unroll
+                for (int v = 0; v < NV; v++) {
+                    n32[4 * v + 0] = nat[v].x; n32[4 * v + 1] = nat[v].y; n32[4 * v + 2] = nat[v].z; n32[4 * v + 3] = nat[v].w;
                 }
-                for (int j = ctid; j < p.n_xsum; j += CT) {
+#pragma unroll
+                for (int f = 0; f < NSB; f++) {
                     float sx = 0.f;
-                    if (live) {
-                        const uint4* src = reinterpret_cast<const uint4*>(xg + (size_t)m * K + (size_t)j * SBC);
 #pragma unroll
-                        for (int v = 0; v < SBC / 8; v++) {
-                            const uint4 t = src[v];
-#pragma unroll
-                            for (int e = 0; e < 4; e++) {
-                                const uint32_t r = comp(t, e);
-                                sx += __uint_as_float(r << 16);
-                                sx += __uint_as_float(r & 0xffff0000u);
-                            }
-                        }
+                    for (int i = 0; i < SBC / 2; i++) {
+                        const uint32_t w32 = n32[f * (SBC / 2) + i];
+                        sx += __uint_as_float(w32 << 16);
+                        sx += __uint_as_float(w32 & 0xffff0000u);
                     }
-                    xsum[(size_t)m * p.n_xsum + j] = sx;
+                    xsum[j][m][f] = sx;
+                }
+#pragma unroll
+                for (int q = 0; q < NP; q++) {
+                    const int ia = pair_a<BITS>(q), ib = pair_b<BITS>(q);
+                    const uint32_t sel = ((ia & 1) ? 0x32u : 0x10u) | (((ib & 1) ? 0x76u : 0x54u) << 8);
+                    xr[j][m][q] = __byte_perm(n32[ia >> 1], n32[ib >> 1], sel);
                 }
             }
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");
 
         const uint32_t ring_u32 = smem_u32(ring);
-        const uint32_t xs_u32 = smem_u32(xs);
-        float yacc[MT];
+        const uint32_t g2 = (uint32_t)p.G * 2u;
+        const int lrow0 = rgi * R;  // first stage-local row of this warp
+        bool all_live = true;       // warp-uniform: every lane of every owned chunk column is inside the row
 #pragma unroll
-        for (int m = 0; m < MT; m++) yacc[m] = 0.f;
-        int cur_row = -1;  // CTA-local row whose partial sums live in yacc
+        for (int j = 0; j < CPW; j++) {
+            const int c = cwi + j * p.cw;
+            all_live = all_live && (c < p.nch) && ((uint32_t)(c + 1) * CHUNK_B <= p.row_bytes);
+        }
 
-        // scale/bias registers for (iteration, piece-of-warp, fragment); prefetched two iterations ahead
-        uint32_t sb_cur[PPW][NSB], sb_nxt[PPW][NSB], sb_nn[PPW][NSB];
-        auto load_sb = [&](int it, uint32_t (&dst)[PPW][NSB]) {
+        // one (row, chunk column) unit: LDS the packed words + scale/bias, unpack, FMA, apply the group affine
+        auto unit = [&](uint32_t slot, int lr, int j, int64_t grow, float (&yrow)[MT]) {
+            const int c = cwi + j * p.cw;
+            const uint32_t waddr = slot + (uint32_t)lr * p.row_bytes + (uint32_t)c * CHUNK_B + (uint32_t)lane * UB;
+            uint32_t w[NW];
 #pragma unroll
-            for (int q = 0; q < PPW; q++) {
-                const int pc = it * PPS + warp * PPW + q;
+            for (int v = 0; v < NW / 4; v++) {
+                const uint4 t = lds128(waddr + 16 * v);
+                w[4 * v + 0] = t.x; w[4 * v + 1] = t.y; w[4 * v + 2] = t.z; w[4 * v + 3] = t.w;
+            }
 #pragma unroll
-                for (int f = 0; f < NSB; f++) dst[q][f] = 0;
-                if (pc < npieces) {
-                    const int r = row_of(pc), c = pc - r * nch;
-                    const uint32_t ubyte = (uint32_t)c * PIECE_B + (uint32_t)lane * UB;
-                    if (ubyte < p.row_bytes) {
-                        const int k0 = (c * 32 + lane) * CPU;
-                        const int64_t gi = (r0 + r) * (int64_t)p.G + (k0 >> p.gs_shift);
+            for (int f = 0; f < NSB; f++) {
+                uint32_t sraw, braw;
+                if constexpr (SB_TMA) {
+                    const uint32_t sa = slot + p.sb_off + (uint32_t)lr * g2 + (uint32_t)(gidx[j] + f) * 2u;
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(sraw) : "r"(sa));
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(braw) : "r"(sa + (uint32_t)p.tr * g2));
+                } else {
+                    const int64_t gi = grow * (int64_t)p.G + gidx[j] + f;
+                    sraw = __ldg(p.scales + gi);
+                    braw = __ldg(p.biases + gi);
+                }
+                float dot[MT];
 #pragma unroll
-                        for (int f = 0; f < NSB; f++) {
-                            const int64_t g = gi + ((f * SBC) >> p.gs_shift);
-                            dst[q][f] = (uint32_t)__ldg(p.scales + g) | ((uint32_t)__ldg(p.biases + g) << 16);
-                        }
-                    }
+                for (int m = 0; m < MT; m++) dot[m] = 0.f;
+#pragma unroll
+                for (int aa = 0; aa < APS; aa++) {
+                    float acc[MT];
+#pragma unroll
+                    for (int m = 0; m < MT; m++) acc[m] = 0.f;
+                    atom_dot<BITS, MT, NP>(w, f * APS + aa, xr[j], acc);
+#pragma unroll
+                    for (int m = 0; m < MT; m++) dot[m] += acc[m];
+                }
+                const float sc = __uint_as_float(sraw << 16);
+                const float bi = __uint_as_float(braw << 16);
+                const float cc = fmaf(-(float)F::OFF, sc, bi);
+#pragma unroll
+                for (int m = 0; m < MT; m++) {
+                    yrow[m] = fmaf(sc, dot[m], yrow[m]);
+                    yrow[m] = fmaf(cc, xsum[j][m][f], yrow[m]);
                 }
             }
         };
-        load_sb(0, sb_cur);
-        load_sb(1, sb_nxt);
 
-        for (int it = 0; it < nstage_iters; it++) {
+        for (int it = 0; it < ns; it++) {
             const int s = it % kStages;
             const uint32_t phase = (uint32_t)(it / kStages) & 1u;
-            load_sb(it + 2, sb_nn);  // in flight across two ring stages
+            const int ra = it * spr;
+            int nr = rows - ra;
+            if (nr > spr) nr = spr;
+            float yacc[R][MT];
+#pragma unroll
+            for (int i = 0; i < R; i++)
+#pragma unroll
+                for (int m = 0; m < MT; m++) yacc[i][m] = 0.f;
 
             mbar_wait(&full_bar[s], phase);
-
-            const int pa = it * PPS;
-            const int ra = row_of(pa), ca = pa - ra * nch;
-            const uint64_t off_a = (uint64_t)ra * p.row_bytes + (uint64_t)ca * PIECE_B;
+            const uint32_t slot = ring_u32 + (uint32_t)s * p.slot_bytes;
+            if (all_live && lrow0 + R <= nr) {
+                // fast path: no predicates, the R rows are independent instruction streams the compiler interleaves
 #pragma unroll
-            for (int q = 0; q < PPW; q++) {
-                const int pc = pa + warp * PPW + q;
-                if (pc < npieces) {  // warp-uniform
-                    const int r = row_of(pc), c = pc - r * nch;
-                    if (r != cur_row) {
-                        if (cur_row >= 0) {
+                for (int i = 0; i < R; i++)
 #pragma unroll
-                            for (int m = 0; m < MT; m++) {
-                                const float v = warp_sum(yacc[m]);
-                                if (lane == 0) atomicAdd(&ysum[cur_row * MT + m], v);
-                                yacc[m] = 0.f;
-                            }
-                        }
-                        cur_row = r;
-                    }
-                    const uint32_t ubyte = (uint32_t)c * PIECE_B + (uint32_t)lane * UB;
-                    if (ubyte < p.row_bytes) {
-                        const uint32_t poff = (uint32_t)((uint64_t)r * p.row_bytes + (uint64_t)c * PIECE_B - off_a);
-                        const uint32_t waddr = ring_u32 + (uint32_t)s * STAGE_B + poff + (uint32_t)lane * UB;
-                        uint32_t w[NW];
+                    for (int j = 0; j < CPW; j++) unit(slot, lrow0 + i, j, r0 + ra + lrow0 + i, yacc[i]);
+            } else {
 #pragma unroll
-                        for (int v = 0; v < NW / 4; v++) {
-                            const uint4 t = lds128(waddr + 16 * v);
-                            w[4 * v + 0] = t.x; w[4 * v + 1] = t.y; w[4 * v + 2] = t.z; w[4 * v + 3] = t.w;
-                        }
-                        const int u = c * 32 + lane;
-                        const uint32_t xaddr = xs_u32 + (uint32_t)(((c * VPU) * 32 + lane) << 4);
+                for (int i = 0; i < R; i++) {
+                    const int lr = lrow0 + i;
+                    if (lr < nr) {  // warp-uniform
 #pragma unroll
-                        for (int f = 0; f < NSB; f++) {
-                            float dot[MT];
-#pragma unroll
-                            for (int m = 0; m < MT; m++) dot[m] = 0.f;
-#pragma unroll
-                            for (int aa = 0; aa < APS; aa++) {
-                                const int a = f * APS + aa;
-                                uint4 xv[MT][F::XPA];
-#pragma unroll
-                                for (int m = 0; m < MT; m++)
-#pragma unroll
-                                    for (int v = 0; v < F::XPA; v++)
-                                        xv[m][v] = lds128(xaddr + (uint32_t)m * p.xs_stride +
-                                                          (uint32_t)((a * F::XPA + v) * 512));
-                                float acc[MT];
-#pragma unroll
-                                for (int m = 0; m < MT; m++) acc[m] = 0.f;
-                                atom_dot<BITS, MT>(w, a, xv, acc);
-#pragma unroll
-                                for (int m = 0; m < MT; m++) dot[m] += acc[m];
-                            }
-                            const uint32_t pk = sb_cur[q][f];
-                            const float sc = __uint_as_float(pk << 16);
-                            const float bi = __uint_as_float(pk & 0xffff0000u);
-                            const float cc = fmaf(-(float)F::OFF, sc, bi);
-#pragma unroll
-                            for (int m = 0; m < MT; m++) {
-                                const float sx = xsum[(size_t)m * p.n_xsum + u * NSB + f];
-                                yacc[m] = fmaf(sc, dot[m], yacc[m]);
-                                yacc[m] = fmaf(cc, sx, yacc[m]);
-                            }
-                        }
+                        for (int j = 0; j < CPW; j++)
+                            if (live[j]) unit(slot, lr, j, r0 + ra + lr, yacc[i]);
                     }
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[s]);
+            if (lane == 0) mbar_arrive(&empty_bar[s]);  // slot free: all of this warp's reads are done
+            // ---- fold the warp's row partials with the butterfly; lane 8*i then owns row i.  Each chunk
+            //      column writes its own slot of ypart (no atomics -> bitwise reproducible results)
+            if (lrow0 < nr) {
 #pragma unroll
-            for (int q = 0; q < PPW; q++)
+                for (int m = 0; m < MT; m++) {
+                    float v4[R];
 #pragma unroll
-                for (int f = 0; f < NSB; f++) {
-                    sb_cur[q][f] = sb_nxt[q][f];
-                    sb_nxt[q][f] = sb_nn[q][f];
+                    for (int i = 0; i < R; i++) v4[i] = yacc[i][m];
+                    const float tot = reduce_rows<R>(v4, lane);
+                    const int lr = lrow0 + (lane >> 3);
+                    if ((lane & 7) == 0 && lr < nr) ysum[((ra + lr) * p.cw + cwi) * MT + m] = tot;
                 }
-        }
-        if (cur_row >= 0) {
-#pragma unroll
-            for (int m = 0; m < MT; m++) {
-                const float v = warp_sum(yacc[m]);
-                if (lane == 0) atomicAdd(&ysum[cur_row * MT + m], v);
             }
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");
-        // ---- epilogue: one rounding to bf16, optional bias as a second rounded add, coalesced store
-        for (int i = ctid; i < rows * MT; i += CT) {
-            const int m = i / rows, r = i - m * rows;
-            if (m < p.M) {
-                float v = __bfloat162float(__float2bfloat16_rn(ysum[r * MT + m]));
-                if (p.bias != nullptr) v = __fadd_rn(v, __bfloat162float(p.bias[r0 + r]));
-                p.y[(size_t)m * p.N + r0 + r] = __float2bfloat16_rn(v);
-            }
+    }
+    __syncthreads();
+    // ---- epilogue: one rounding to bf16, optional bias as a second rounded add, coalesced store
+    for (int i = threadIdx.x; i < rows * MT; i += kThreads) {
+        const int m = i / rows, r = i - m * rows;
+        if (m < p.M) {
+            float tot = 0.f;
+            for (int c = 0; c < p.cw; c++) tot += ysum[(r * p.cw + c) * MT + m];
+            float v = __bfloat162float(__float2bfloat16_rn(tot));
+            if (p.bias != nullptr) v = __fadd_rn(v, __bfloat162float(p.bias[r0 + r]));
+            p.y[(size_t)m * p.N + r0 + r] = __float2bfloat16_rn(v);
         }
     }
 }
 
-template <int BITS, int NSB, int MT>
+template <int BITS, int NSB, int MT, int CPW, bool SB_TMA>
 int launch_inst(const GemvParams& p, size_t smem_bytes, int grid, cudaStream_t st) {
     static bool configured = false;  // benign race: attribute set is idempotent
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemv_kernel<BITS, NSB, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(gemv_kernel<BITS, NSB, MT, CPW, SB_TMA>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return check_cuda(e);
         configured = true;
     }
-    gemv_kernel<BITS, NSB, MT><<<grid, kThreads, smem_bytes, st>>>(p);
+    gemv_kernel<BITS, NSB, MT, CPW, SB_TMA><<<grid, kThreads, smem_bytes, st>>>(p);
     count_launch();
     return check_cuda(cudaGetLastError());
 }
 
-template <int BITS> constexpr int nsb_for(int gs) {
-    return Fmt<BITS>::CPU > gs ? Fmt<BITS>::CPU / gs : 1;
-}
+template <int BITS> constexpr int nsb_for(int gs) { return Fmt<BITS>::CPU > gs ? Fmt<BITS>::CPU / gs : 1; }
+template <int BITS> constexpr int max_cpw() { return BITS == 8 ? 4 : (BITS == 4 ? 2 : 1); }
 
 struct Plan {
     bool ok;
-    int mt;
+    int mt, cpw, nch, cw, rg, tr;
+    bool sb_tma;
+    uint32_t slot_bytes, sb_off;
     size_t smem;
-    int nch, n_xsum;
-    uint32_t xs_stride;
 };
 
 template <int BITS> Plan make_plan(int64_t M, int64_t N, int64_t K, int gs) {
     using F = Fmt<BITS>;
     Plan pl{};
     const int64_t row_bytes = K * BITS / 8;
-    if (row_bytes % F::UB) return pl;
-    const int nsb = nsb_for<BITS>(gs);
-    const int sbc = F::CPU / nsb;
-    const int piece_b = 32 * F::UB;
-    pl.nch = (int)((row_bytes + piece_b - 1) / piece_b);
-    pl.n_xsum = (int)(K / sbc);
-    pl.xs_stride = (uint32_t)pl.nch * 32u * F::CPU * 2u;
+    if (row_bytes % F::UB || row_bytes % 16 || row_bytes > kStageWBytes) return pl;
+    const int chunk_b = 32 * F::UB;
+    pl.nch = (int)((row_bytes + chunk_b - 1) / chunk_b);
+    // warp grid: as many chunk columns as fit in 16 warps (each warp owning cpw columns), the rest row groups
+    pl.cpw = (pl.nch + kConsumerWarps - 1) / kConsumerWarps;
+    if (pl.cpw == 3) pl.cpw = 4;
+    if (pl.cpw > max_cpw<BITS>()) return pl;
+    pl.cw = (pl.nch + pl.cpw - 1) / pl.cpw;
+    pl.rg = kConsumerWarps / pl.cw;
+    const int64_t tr_fit = kStageWBytes / row_bytes;  // >= 1
+    if ((int64_t)pl.rg * kRowsPerWarp > tr_fit) pl.rg = (int)((tr_fit + kRowsPerWarp - 1) / kRowsPerWarp);
+    if (pl.rg < 1) pl.rg = 1;
+    pl.tr = (int)(tr_fit < (int64_t)pl.rg * kRowsPerWarp ? tr_fit : (int64_t)pl.rg * kRowsPerWarp);
     const int grid = device_sm_count();
     if ((N + grid - 1) / grid > kMaxRowsPerCta) return pl;
-    for (int mt = (M >= 2 ? 2 : 1); mt >= 1; mt--) {
-        size_t smem = (size_t)kStages * F::PPS * piece_b + (size_t)mt * pl.xs_stride + (((size_t)mt * pl.n_xsum + 3) & ~(size_t)3) * 4 +
-                      (size_t)kMaxRowsPerCta * mt * 4 + 2 * kStages * 8 + 16;
-        if (smem <= 227 * 1024) {
-            pl.ok = true;
-            pl.mt = mt;
-            pl.smem = smem;
-            return pl;
-        }
-    }
+    const int64_t G = K / gs;
+    pl.sb_tma = (G * 2) % 16 == 0;
+    const uint32_t wpart = (uint32_t)(((int64_t)pl.tr * row_bytes + 127) & ~(int64_t)127);
+    pl.sb_off = wpart;
+    pl.slot_bytes = wpart + (pl.sb_tma ? (uint32_t)((2 * (int64_t)pl.tr * G * 2 + 127) & ~(int64_t)127) : 0u);
+    pl.mt = (M >= 2 && BITS != 3) ? 2 : 1;  // 3-bit units hold 64 activation registers per token
+    const int64_t rows_max = (N + grid - 1) / grid;
+    pl.smem = (size_t)kStages * pl.slot_bytes + 2 * kStages * 8 + (size_t)rows_max * pl.cw * pl.mt * 4 + 16;
+    if (pl.smem > 227 * 1024) return pl;
+    pl.ok = true;
     return pl;
+}
+
+template <int BITS, int NSB, int MT, int CPW>
+int launch_sb(const GemvParams& p, const Plan& pl, int grid, cudaStream_t st) {
+    return pl.sb_tma ? launch_inst<BITS, NSB, MT, CPW, true>(p, pl.smem, grid, st)
+                     : launch_inst<BITS, NSB, MT, CPW, false>(p, pl.smem, grid, st);
+}
+
+template <int BITS, int NSB, int MT>
+int launch_cpw(const GemvParams& p, const Plan& pl, int grid, cudaStream_t st) {
+    if (pl.cpw == 1) return launch_sb<BITS, NSB, MT, 1>(p, pl, grid, st);
+    if constexpr (max_cpw<BITS>() >= 2) {
+        if (pl.cpw == 2) return launch_sb<BITS, NSB, MT, 2>(p, pl, grid, st);
+    }
+    if constexpr (max_cpw<BITS>() >= 4) {
+        if (pl.cpw == 4) return launch_sb<BITS, NSB, MT, 4>(p, pl, grid, st);
+    }
+    return GBXQ_EUNSUPPORTED;
+}
+
+template <int BITS, int NSB>
+int launch_mt(const GemvParams& p, const Plan& pl, int grid, cudaStream_t st) {
+    if constexpr (BITS != 3) {
+        if (pl.mt == 2) return launch_cpw<BITS, NSB, 2>(p, pl, grid, st);
+    }
+    return launch_cpw<BITS, NSB, 1>(p, pl, grid, st);
 }
 
 template <int BITS>
@@ -468,9 +508,11 @@ int launch_bits(const void* x, const uint32_t* w, const void* s, const void* b, 
     p.G = (int)(K / gs);
     p.row_bytes = (uint32_t)(K * BITS / 8);
     p.nch = pl.nch;
-    p.nch_mul = pl.nch > 1 ? (uint32_t)((((uint64_t)1) << 32) / (uint64_t)pl.nch) + 1u : 0u;
-    p.xs_stride = pl.xs_stride;
-    p.n_xsum = pl.n_xsum;
+    p.cw = pl.cw;
+    p.rg = pl.rg;
+    p.tr = pl.tr;
+    p.slot_bytes = pl.slot_bytes;
+    p.sb_off = pl.sb_off;
     const int nsb = nsb_for<BITS>(gs);
     int grid = device_sm_count();
     if (grid > N) grid = (int)N;
@@ -479,17 +521,13 @@ int launch_bits(const void* x, const uint32_t* w, const void* s, const void* b, 
         p.y = reinterpret_cast<__nv_bfloat16*>(y) + m0 * N;
         p.M = (int)((M - m0) < pl.mt ? (M - m0) : pl.mt);
         int rc = GBXQ_EUNSUPPORTED;
-#define GBXQ_GEMV_CASE(NSB_)                                                           \
-    if (nsb == NSB_) {                                                                 \
-        if constexpr (Fmt<BITS>::ATOMS % NSB_ == 0 && NSB_ <= Fmt<BITS>::CPU / 32 + (BITS == 8)) { \
-            rc = pl.mt == 2 ? launch_inst<BITS, NSB_, 2>(p, pl.smem, grid, st)         \
-                            : launch_inst<BITS, NSB_, 1>(p, pl.smem, grid, st);        \
-        }                                                                              \
-    }
-        GBXQ_GEMV_CASE(1)
-        GBXQ_GEMV_CASE(2)
-        GBXQ_GEMV_CASE(4)
-#undef GBXQ_GEMV_CASE
+        if (nsb == 1) rc = launch_mt<BITS, 1>(p, pl, grid, st);
+        if constexpr (Fmt<BITS>::CPU >= 64) {
+            if (nsb == 2) rc = launch_mt<BITS, 2>(p, pl, grid, st);
+        }
+        if constexpr (Fmt<BITS>::CPU >= 128) {
+            if (nsb == 4) rc = launch_mt<BITS, 4>(p, pl, grid, st);
+        }
         if (rc != GBXQ_OK) return rc;
     }
     return GBXQ_OK;

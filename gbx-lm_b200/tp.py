@@ -1,0 +1,148 @@
+"""Tensor-parallel sharding of the QuantizedLinear projections (the reference itself
+has no TP -- section 2.2 -- this is the new work BASELINE.json's north_star defines).
+
+  column-parallel  q_proj k_proj v_proj gate_proj up_proj : split N (rows of qweight/scales/zeros, bias)
+  row-parallel     o_proj down_proj                       : split K (packed columns at (K/tp)*bits/32
+                                                            words, scale columns at K/(tp*gs)) and sum
+                                                            the partial [M, hidden] outputs across ranks
+
+Pure slicing -- no re-packing -- legal iff (K/tp) % group_size == 0 and (K/tp)*bits % 32 == 0.
+One process per GPU; the collective is NCCL over NVLink (`torch.distributed`), or the library's
+one-shot peer-memory all-reduce (`gbxq_allreduce_oneshot`) for the latency-bound decode messages.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+COLUMN_PARALLEL = ("q_proj", "k_proj", "v_proj", "gate_proj", "up_proj")
+ROW_PARALLEL = ("o_proj", "down_proj")
+
+
+class TPContext:
+    """Rank/world of the tensor-parallel group + the all-reduce used after row-parallel layers."""
+
+    def __init__(self, rank: int = 0, world: int = 1, group=None, oneshot: "Optional[OneShotAllReduce]" = None):
+        self.rank = rank
+        self.world = world
+        self.group = group
+        self.oneshot = oneshot
+
+    def all_reduce(self, y: torch.Tensor) -> torch.Tensor:
+        if self.world == 1:
+            return y
+        if self.oneshot is not None and y.is_cuda and self.oneshot.fits(y):
+            return self.oneshot(y)
+        import torch.distributed as dist
+
+        dist.all_reduce(y, group=self.group)
+        return y
+
+
+def proj_kind(name: str) -> Optional[str]:
+    for p in COLUMN_PARALLEL:
+        if f".{p}." in name or name.endswith("." + p):
+            return "column"
+    for p in ROW_PARALLEL:
+        if f".{p}." in name or name.endswith("." + p):
+            return "row"
+    return None
+
+
+def check_row_split(k: int, bits: int, group_size: int, world: int):
+    if k % world or (k // world) % group_size or ((k // world) * bits) % 32:
+        raise ValueError(
+            f"row-parallel split of K={k} over {world} ranks needs (K/tp) % group_size == 0 and "
+            f"(K/tp)*bits % 32 == 0 (bits={bits}, group_size={group_size})"
+        )
+
+
+def shard_tensor(name: str, t: torch.Tensor, bits: int, group_size: int, rank: int, world: int) -> torch.Tensor:
+    """Slice one checkpoint tensor of a QuantizedLinear (`<module>.{qweight,scales,zeros,bias}`) for `rank`."""
+    if world == 1:
+        return t
+    kind = proj_kind(name.rsplit(".", 1)[0])
+    leaf = name.rsplit(".", 1)[1]
+    if kind is None or leaf not in ("qweight", "scales", "zeros", "bias"):
+        return t
+    if kind == "column":
+        n = t.shape[0]
+        if n % world:
+            raise ValueError(f"{name}: N={n} not divisible by tp={world}")
+        per = n // world
+        return t[rank * per : (rank + 1) * per].contiguous()
+    # row-parallel
+    if leaf == "bias":
+        # added once: rank 0 keeps it, the others add zero
+        return t if rank == 0 else torch.zeros_like(t)
+    if leaf == "qweight":
+        k = t.shape[1] * 32 // bits
+        check_row_split(k, bits, group_size, world)
+        per = (k // world) * bits // 32
+    else:
+        k = t.shape[1] * group_size
+        check_row_split(k, bits, group_size, world)
+        per = (k // world) // group_size
+    return t[:, rank * per : (rank + 1) * per].contiguous()
+
+
+def shard_state_dict(weights: Dict[str, torch.Tensor], bits_of, rank: int, world: int) -> Dict[str, torch.Tensor]:
+    """bits_of(module_name) -> (bits, group_size) for every QuantizedLinear module name."""
+    if world == 1:
+        return weights
+    out = {}
+    for k, v in weights.items():
+        mod = k.rsplit(".", 1)[0]
+        if proj_kind(mod) is not None:
+            b, g = bits_of(mod)
+            out[k] = shard_tensor(k, v, b, g, rank, world)
+        else:
+            out[k] = v
+    return out
+
+
+class OneShotAllReduce:
+    """Latency-optimised sum all-reduce over NVLink peer memory (gbxq_allreduce_oneshot): staging
+    buffers and flags live in torch symmetric memory so every rank can address every peer."""
+
+    def __init__(self, group, device: torch.device, capacity_elems: int = 1 << 20, dtype=torch.bfloat16):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        from . import _lib
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.world = dist.get_world_size(self.group)
+        self.dtype = dtype
+        self.capacity = capacity_elems
+        self.buf = symm.empty((capacity_elems,), dtype=dtype, device=device)
+        self.hdl = symm.rendezvous(self.buf, self.group.group_name)
+        self.flags = symm.empty((self.world * _lib.AR_MAX_CTAS,), dtype=torch.int32, device=device)
+        self.flags.zero_()
+        self.fhdl = symm.rendezvous(self.flags, self.group.group_name)
+        bufs = [self.hdl.buffer_ptrs[r] for r in range(self.world)]
+        flgs = [self.fhdl.buffer_ptrs[r] for r in range(self.world)]
+        self.bufs_dev = torch.tensor(bufs, dtype=torch.int64, device=device)
+        self.flags_dev = torch.tensor(flgs, dtype=torch.int64, device=device)
+        self.seq = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)
+
+    def fits(self, y: torch.Tensor) -> bool:
+        return y.dtype == self.dtype and y.numel() * 2 <= self.capacity and (y.numel() * y.element_size()) % 16 == 0
+
+    def __call__(self, y: torch.Tensor) -> torch.Tensor:
+        from . import _lib
+
+        y = y.contiguous()
+        self.seq += 1
+        dt = {torch.bfloat16: 0, torch.float16: 1, torch.float32: 2}[y.dtype]
+        st = torch.cuda.current_stream().cuda_stream
+        rc = _lib.get().gbxq_allreduce_oneshot(
+            y.data_ptr(), y.data_ptr(), y.numel(), dt, self.bufs_dev.data_ptr(), self.flags_dev.data_ptr(),
+            self.capacity, self.rank, self.world, self.seq, st,
+        )
+        _lib.check(rc, "gbxq_allreduce_oneshot")
+        return y
