@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgbxq.so")
 
 BF16, F16, F32 = 0, 1, 2
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_GEMV, KERNEL_GEMM = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_GEMV, KERNEL_GEMM, KERNEL_SKINNY = 0, 1, 2, 3, 4
 AR_MAX_CTAS = 32
 
 EXPORTS = (

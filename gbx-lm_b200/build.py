@@ -21,6 +21,7 @@ SOURCES = [
     "gbxq_dequant.cu",
     "gbxq_generic.cu",
     "gbxq_gemv.cu",
+    "gbxq_skinny.cu",
     "gbxq_gemm_sm100.cu",
     "gbxq_allreduce.cu",
 ]

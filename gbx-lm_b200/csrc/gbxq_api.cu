@@ -27,14 +27,20 @@ int device_sm_count() {
 
 // M above which the tensor-core kernel takes over from the streaming GEMV.  The GEMV re-streams
 // the weights once per 2 tokens, the GEMM dequantises each weight once per <=256 tokens.
-static constexpr int64_t kGemvMaxM = 4;
+static constexpr int64_t kSkinnyMaxM = 16;  // 2 passes of 8 tokens; above that the tcgen05 GEMM amortises better
 
 static int select(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype, const void* x, const void* w,
                   const void* y) {
+    const bool skinny_ok = skinny_supported(M, N, K, bits, gs, dtype, x, w, y);
     const bool gemv_ok = gemv_supported(M, N, K, bits, gs, dtype, x, w, y);
     const bool gemm_ok = gemm_supported(M, N, K, bits, gs, dtype, x, w, y);
-    if (gemv_ok && (M <= kGemvMaxM || !gemm_ok)) return GBXQ_KERNEL_GEMV;
+    // measured on B200 (profiles/): the FMA-pipe GEMV wins at M <= 2, the tensor-pipe skinny kernel costs the
+    // same for 1..8 tokens and wins from M = 3
+    if (gemv_ok && M <= 2) return GBXQ_KERNEL_GEMV;
+    if (skinny_ok && (M <= kSkinnyMaxM || !gemm_ok)) return GBXQ_KERNEL_SKINNY;
+    if (gemv_ok && (M <= 4 || !gemm_ok)) return GBXQ_KERNEL_GEMV;  // 3-/6-bit packings and odd shapes
     if (gemm_ok) return GBXQ_KERNEL_GEMM;
+    if (gemv_ok) return GBXQ_KERNEL_GEMV;
     return GBXQ_KERNEL_GENERIC;
 }
 
@@ -97,6 +103,9 @@ int gbxq_qmm_ex(const void* x, const uint32_t* qweight, const void* scales, cons
         case GBXQ_KERNEL_GEMV:
             if (!gemv_supported(M, N, K, bits, group_size, dtype, x, qweight, y)) return GBXQ_EUNSUPPORTED;
             return launch_gemv(x, qweight, scales, biases, bias, y, M, N, K, bits, group_size, st);
+        case GBXQ_KERNEL_SKINNY:
+            if (!skinny_supported(M, N, K, bits, group_size, dtype, x, qweight, y)) return GBXQ_EUNSUPPORTED;
+            return launch_skinny(x, qweight, scales, biases, bias, y, M, N, K, bits, group_size, st);
         case GBXQ_KERNEL_GEMM:
             if (!gemm_supported(M, N, K, bits, group_size, dtype, x, qweight, y)) return GBXQ_EUNSUPPORTED;
             return launch_gemm(x, qweight, scales, biases, bias, y, M, N, K, bits, group_size, st);

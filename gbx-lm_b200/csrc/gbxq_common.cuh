@@ -155,6 +155,10 @@ bool gemv_supported(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype
                     const void* y);
 int launch_gemv(const void* x, const uint32_t* w, const void* s, const void* b, const void* bias, void* y, int64_t M,
                 int64_t N, int64_t K, int bits, int gs, cudaStream_t st);
+bool skinny_supported(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype, const void* x, const void* w,
+                      const void* y);
+int launch_skinny(const void* x, const uint32_t* w, const void* s, const void* b, const void* bias, void* y, int64_t M,
+                  int64_t N, int64_t K, int bits, int gs, cudaStream_t st);
 bool gemm_supported(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype, const void* x, const void* w,
                     const void* y);
 int launch_gemm(const void* x, const uint32_t* w, const void* s, const void* b, const void* bias, void* y, int64_t M,

@@ -66,8 +66,9 @@ typedef enum gbxq_dtype { GBXQ_BF16 = 0, GBXQ_F16 = 1, GBXQ_F32 = 2 } gbxq_dtype
 typedef enum gbxq_kernel {
     GBXQ_KERNEL_AUTO = 0,
     GBXQ_KERNEL_GENERIC = 1, /* shape-agnostic warp-per-row kernel (all dtypes)            */
-    GBXQ_KERNEL_GEMV = 2,    /* TMA-bulk ring streaming GEMV, M tiles of 1/2 (bf16)         */
-    GBXQ_KERNEL_GEMM = 3     /* tcgen05/TMEM tensor-core GEMM with in-kernel dequant (bf16) */
+    GBXQ_KERNEL_GEMV = 2,    /* TMA-bulk ring streaming GEMV on the FMA pipe, M tiles of 1/2 */
+    GBXQ_KERNEL_GEMM = 3,    /* tcgen05/TMEM tensor-core GEMM with in-kernel dequant (bf16) */
+    GBXQ_KERNEL_SKINNY = 4   /* mma.sync skinny matmul, 8 tokens per pass, 2/4/8-bit (bf16)  */
 } gbxq_kernel;
 
 /* Library / ABI identification. */

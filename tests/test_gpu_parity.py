@@ -87,13 +87,31 @@ def _run_case(g, dev, kernel, bits, gs, M, N, K, seed, with_bias=False):
     return assert_close_to_truth(y, ref, f"{kernel} b{bits} g{gs} M{M} N{N} K{K}")
 
 
-@pytest.mark.parametrize("kernel", ["generic", "gemv"])
+def _skinny_ok(bits, gs):
+    return bits in (2, 4, 8) and not (bits == 2 and gs == 32)
+
+
+@pytest.mark.parametrize("kernel", ["generic", "gemv", "skinny"])
 @pytest.mark.parametrize("bits", BITS)
 @pytest.mark.parametrize("gs", GS)
 def test_qmm_vs_oracle_small(cuda_device, kernel, bits, gs):
     g = _ops()
-    for M in (1, 2, 3):
+    if kernel == "skinny" and not _skinny_ok(bits, gs):
+        with pytest.raises(RuntimeError):  # forcing a kernel that cannot serve the arguments is an error, not a fallback
+            _run_case(g, cuda_device, kernel, bits, gs, 1, 70, 1024, seed=1)
+        return
+    for M in (1, 2, 3) + ((8, 9) if kernel == "skinny" else ()):
         _run_case(g, cuda_device, kernel, bits, gs, M, 70, 1024, seed=bits * 31 + gs + M)
+
+
+@pytest.mark.parametrize("bits", (2, 4, 8))
+def test_qmm_skinny_model_shapes(cuda_device, bits):
+    """mma.sync skinny kernel on the config shapes: ragged k-tiles (3584/64 = 56 groups = 3.5 tiles),
+    row counts that are not multiples of 16 or of the grid, every token count 1..8 and a 2-pass 13."""
+    g = _ops()
+    for (N, K) in ((300, 4096), (96, 14336), (150, 3584), (1, 2048), (147, 8192), (149, 3072), (5000, 512)):
+        for M in (1, 4, 7, 8, 13):
+            _run_case(g, cuda_device, "skinny", bits, 64, M, N, K, seed=N + K + bits + M, with_bias=(M == 7))
 
 
 @pytest.mark.parametrize("bits", BITS)
@@ -125,7 +143,9 @@ def test_qmm_golden_fixtures(cuda_device, case):
     z = bf16_from_bits(np.array(case["zeros_bf16"], dtype=np.uint16), cuda_device)
     x = bf16_from_bits(np.array(case["x_bf16"], dtype=np.uint16), cuda_device)
     gold = A.bf16_bits_to_f32(np.array(case["y_bf16"], dtype=np.uint16))
-    for kernel in ("generic", "gemv"):
+    for kernel in ("generic", "gemv", "skinny"):
+        if kernel == "skinny" and not _skinny_ok(case["bits"], case["group_size"]):
+            continue
         y = g.quantized_matmul(x, w, s, z, True, case["group_size"], case["bits"], kernel=kernel).float().cpu().numpy()
         ulp = np.maximum(np.abs(gold) * 2.0 ** -7, np.abs(gold).max() * 2.0 ** -9)
         assert (np.abs(y - gold) <= ulp).all(), kernel
@@ -214,9 +234,14 @@ def test_full_size_8b_gate_proj_properties(cuda_device):
     y0 = g.quantized_matmul(x[:, :h].contiguous(), qw[:, :wh].contiguous(), s[:, : h // gs].contiguous(), z[:, : h // gs].contiguous(), True, gs, bits)
     y1 = g.quantized_matmul(x[:, h:].contiguous(), qw[:, wh:].contiguous(), s[:, h // gs :].contiguous(), z[:, h // gs :].contiguous(), True, gs, bits)
     assert (y.float() - (y0.float() + y1.float())).abs().max() <= 2.0 ** -6 * y.float().abs().max()
-    # M=1 equals the first row of the M=2 call (rows of x are independent)
+    # M=1 equals the first row of the M=2 call (rows of x are independent; reductions are order-fixed)
     y_m1 = g.quantized_matmul(x[:1], qw, s, z, True, gs, bits, kernel="gemv")
     assert torch.equal(y_m1, y[:1])
+    # the tensor-pipe skinny kernel agrees with the FMA-pipe GEMV to bf16 resolution, and with itself bit for bit
+    ys = g.quantized_matmul(x, qw, s, z, True, gs, bits, kernel="skinny")
+    assert (ys.float() - y.float()).abs().max() <= 2.0 ** -7 * y.float().abs().max()
+    assert torch.equal(ys, g.quantized_matmul(x, qw, s, z, True, gs, bits, kernel="skinny"))
+    assert torch.equal(ys[:1], g.quantized_matmul(x[:1], qw, s, z, True, gs, bits, kernel="skinny"))
 
 
 def test_cuda_graph_capture(cuda_device):
