@@ -1,0 +1,94 @@
+"""GPU tests of the CALLERS of the hot path: checkpoint -> load_model ->
+Llama / Qwen2 forward through libgbxq, against an independent fp32 reference on oracle-dequantised
+weights; greedy decode (CUDA-graph vs eager, teacher-forced top-1 vs the reference)."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from gbx_lm_b200 import QuantizedLinear, utils, workloads as W
+from tests import ref_model
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ("tiny-llama", "bpw-4.0", 4, 64),
+    ("tiny-llama", "bpw-2.2", 2, 128),
+    ("tiny-qwen2", None, 4, 128),
+]
+
+
+def _make(tmp_path, name, strat_name, bits, gs, seed=7):
+    dims = W.MODELS[name]
+    strat = W.STRATEGIES[strat_name](dims.layers) if strat_name else None
+    cfg = utils.write_synthetic_checkpoint(tmp_path, dims, strat, seed=seed, default_bits=bits, default_gs=gs, embed_scale=1.0)
+    from safetensors.torch import load_file
+
+    ckpt = load_file(str(tmp_path / "model.safetensors"))
+    plan = {}
+    for (i, p, n, k, b, g) in W.layer_plan(dims, strat, bits, gs):
+        sub = "self_attn" if p in ("q_proj", "k_proj", "v_proj", "o_proj") else "mlp"
+        plan[f"model.layers.{i}.{sub}.{p}"] = (b, g)
+    dense = ref_model.dense_weights(ckpt, lambda m: plan[m])
+    return dims, cfg, dense
+
+
+@pytest.mark.parametrize("name,strat,bits,gs", CASES)
+def test_forward_matches_reference(cuda_device, tmp_path, name, strat, bits, gs):
+    dims, cfg, dense = _make(tmp_path, name, strat, bits, gs)
+    model, _ = utils.load_model(tmp_path, device=cuda_device)
+    assert all(m.qweight.is_cuda for m in model.modules() if isinstance(m, QuantizedLinear))
+    toks = torch.randint(0, dims.vocab, (2, 19), generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        logits = model(toks.to(cuda_device)).float().cpu()
+        ref = ref_model.forward(dense, cfg, toks)
+    assert logits.shape == ref.shape == (2, 19, dims.vocab)
+    err = (logits - ref).abs().max() / ref.abs().max()
+    assert err < 3e-2, err
+    # top-1 agrees wherever the reference's margin is not a rounding tie
+    top2 = ref.topk(2, -1).values
+    clear = (top2[..., 0] - top2[..., 1]) > 0.05 * ref.abs().max()
+    assert (logits.argmax(-1)[clear] == ref.argmax(-1)[clear]).all()
+
+
+def test_chunked_prefill_and_cache_consistency(cuda_device, tmp_path):
+    dims, cfg, dense = _make(tmp_path, "tiny-llama", "bpw-4.0", 4, 64)
+    model, _ = utils.load_model(tmp_path, device=cuda_device)
+    from gbx_lm_b200 import qllama
+
+    toks = torch.randint(0, dims.vocab, (1, 24), generator=torch.Generator().manual_seed(2)).to(cuda_device)
+    with torch.no_grad():
+        full = model(toks).float()
+        cache = qllama.make_prompt_cache(model, 1, 64)
+        a = model(toks[:, :9], cache).float()
+        b = model(toks[:, 9:20], cache).float()
+        outs = [a, b]
+        for i in range(20, 24):
+            outs.append(model(toks[:, i:i + 1], cache).float())
+        inc = torch.cat(outs, 1)
+    assert cache[0].offset == 24
+    assert (inc - full).abs().max() <= 2e-2 * full.abs().max()
+
+
+@pytest.mark.parametrize("name,strat,bits,gs", CASES[:1] + CASES[2:])
+def test_greedy_decode_graph_equals_eager_and_reference(cuda_device, tmp_path, name, strat, bits, gs):
+    dims, cfg, dense = _make(tmp_path, name, strat, bits, gs, seed=11)
+    model, _ = utils.load_model(tmp_path, device=cuda_device)
+    prompt = torch.randint(0, dims.vocab, (12,), generator=torch.Generator().manual_seed(3))
+    g_toks, stats = utils.generate_tokens(model, prompt, max_tokens=48, use_cuda_graph=True)
+    e_toks, _ = utils.generate_tokens(model, prompt, max_tokens=48, use_cuda_graph=False)
+    assert len(g_toks) == 48 and stats["generation_tps"] > 0
+    assert g_toks == e_toks  # the graph replays exactly the eager computation
+    # chunked prefill (utils.py:312-319 semantics) does not change the tokens
+    c_toks, _ = utils.generate_tokens(model, prompt, max_tokens=16, prefill_step_size=5)
+    assert c_toks == g_toks[:16]
+    # teacher-forced check against the fp32 reference: our token is the reference's top-1 wherever the
+    # reference's top-1 margin exceeds bf16 noise; report how many steps had a clear margin
+    seq = torch.cat([prompt, torch.tensor(g_toks)])[None]
+    with torch.no_grad():
+        ref = ref_model.forward(dense, cfg, seq)[0, len(prompt) - 1:-1]
+    top2 = ref.topk(2, -1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 0.05 * ref.abs().max()
+    assert clear.sum() >= 24, f"only {int(clear.sum())} decisive steps"
+    assert (ref.argmax(-1)[clear] == torch.tensor(g_toks)[clear]).all()

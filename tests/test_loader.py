@@ -1,0 +1,166 @@
+"""CPU tests of the host logic around the path: checkpoint layout (gba2mlx format), layer-mix loader
+(strategy -> per-layer bits/group_size), shard slicing for tensor parallelism.  No GPU compute."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gbx_lm_b200 import QuantizedLinear, packing, tp as tpmod, utils, workloads as W
+from oracle import mlx_affine as A
+
+
+@pytest.fixture(scope="module")
+def tiny_ckpt(tmp_path_factory):
+    d = tmp_path_factory.mktemp("tiny_llama")
+    dims = W.MODELS["tiny-llama"]
+    strat = W.strategy_bpw22(dims.layers)
+    utils.write_synthetic_checkpoint(d, dims, strat, seed=3, default_bits=2, default_gs=128)
+    return d, dims, strat
+
+
+def test_checkpoint_layout_matches_gba2mlx(tiny_ckpt):
+    d, dims, strat = tiny_ckpt
+    from safetensors import safe_open
+
+    assert (d / "config.json").exists() and (d / "quant_strategy.json").exists()
+    assert (d / "model.safetensors").exists() and (d / "model.safetensors.index.json").exists()
+    cfg = json.load(open(d / "config.json"))
+    assert cfg["quantization"] == {"group_size": 128, "bits": 2} and list(cfg) == sorted(cfg)
+    with safe_open(str(d / "model.safetensors"), "pt") as f:
+        assert f.metadata() == {"format": "mlx"}
+        keys = set(f.keys())
+        assert "model.embed_tokens.weight" in keys and "model.norm.weight" in keys and "lm_head.weight" not in keys
+        for p in W.PROJS:
+            sub = "self_attn" if p in ("q_proj", "k_proj", "v_proj", "o_proj") else "mlp"
+            for leaf in ("qweight", "scales", "zeros"):
+                assert f"model.layers.0.{sub}.{p}.{leaf}" in keys
+        qw = f.get_tensor("model.layers.0.self_attn.v_proj.qweight")  # 6-bit gs64 in layer 0 of bpw-2.2
+        assert qw.dtype == torch.uint32 and qw.shape == (dims.kv_heads * dims.head_dim, dims.hidden * 6 // 32)
+        assert f.get_tensor("model.layers.0.self_attn.v_proj.scales").dtype == torch.bfloat16
+    idx = json.load(open(d / "model.safetensors.index.json"))
+    assert set(idx["weight_map"].values()) == {"model.safetensors"} and idx["metadata"]["total_size"] > 0
+
+
+def test_load_model_applies_layer_mix_strategy(tiny_ckpt):
+    d, dims, strat = tiny_ckpt
+    model, cfg = utils.load_model(d, device="cpu")
+    plan = {(i, p): (b, g) for (i, p, n, k, b, g) in W.layer_plan(dims, strat)}
+    seen = 0
+    for name, m in model.named_modules():
+        if isinstance(m, QuantizedLinear):
+            i = int(name.split(".")[2])
+            p = name.split(".")[-1]
+            assert (m.bits, m.group_size) == plan[(i, p)], name
+            assert m.qweight.shape == (m.output_dims, m.input_dims // 32 * m.bits)
+            assert m.scales.shape == (m.output_dims, m.input_dims // m.group_size)
+            assert m.scales.dtype == torch.bfloat16 and m.qweight.dtype == torch.uint32
+            assert int(m.qweight.view(torch.int32).abs().sum()) != 0  # weights really loaded
+            seen += 1
+    assert seen == 7 * dims.layers
+    bits_seen = {m.bits for m in model.modules() if isinstance(m, QuantizedLinear)}
+    assert bits_seen == {2, 3, 6}
+    assert model.model.embed_tokens.weight.dtype == torch.bfloat16
+
+
+def test_load_model_without_strategy_uses_config_quantization(tmp_path):
+    dims = W.MODELS["tiny-qwen2"]
+    utils.write_synthetic_checkpoint(tmp_path, dims, None, seed=1, default_bits=4, default_gs=128)
+    assert not (tmp_path / "quant_strategy.json").exists()
+    model, cfg = utils.load_model(tmp_path, device="cpu")
+    for m in model.modules():
+        if isinstance(m, QuantizedLinear):
+            assert (m.bits, m.group_size) == (4, 128)
+    attn = model.model.layers[0].self_attn
+    assert attn.q_proj.bias is not None and attn.k_proj.bias is not None and attn.o_proj.bias is None  # qqwen2.py:44-47
+    assert hasattr(model, "lm_head")  # untied
+
+
+def test_load_errors(tmp_path):
+    with pytest.raises(FileNotFoundError):
+        utils.load_model(tmp_path, device="cpu")  # no config.json
+    json.dump({"model_type": "llama"}, open(tmp_path / "config.json", "w"))
+    with pytest.raises(FileNotFoundError):
+        utils.load_model(tmp_path, device="cpu")  # no safetensors
+    dims = W.MODELS["tiny-llama"]
+    utils.write_synthetic_checkpoint(tmp_path, dims, None, seed=1)
+    cfg = json.load(open(tmp_path / "config.json"))
+    cfg["model_type"] = "mamba"
+    json.dump(cfg, open(tmp_path / "config.json", "w"))
+    with pytest.raises(ValueError):
+        utils.load_model(tmp_path, device="cpu")
+    cfg["model_type"] = "llama"
+    cfg["quantization"] = {"group_size": 48, "bits": 4}
+    json.dump(cfg, open(tmp_path / "config.json", "w"))
+    with pytest.raises(AssertionError):
+        utils.load_model(tmp_path, device="cpu")
+
+
+def test_strategy_missing_entry_raises(tiny_ckpt):
+    d, dims, strat = tiny_ckpt
+    import copy
+
+    bad = copy.deepcopy(strat["measurement"])
+    del bad["model.layers.1"]["down_proj"]
+    model, _ = utils.load_model(d, device="cpu")
+    with pytest.raises(KeyError):
+        QuantizedLinear.reinit_module(model, 128, 2, strategy=bad)
+
+
+def test_make_shards_counts():
+    w = {f"w{i}": torch.zeros(1 << 18, dtype=torch.float32) for i in range(8)}  # 1 MiB each
+    assert len(utils.make_shards(w, max_file_size_gb=5)) == 1
+    shards = utils.make_shards(w, max_file_size_gb=0)  # 0 GiB cap -> one tensor per shard (+ leading empty)
+    assert sum(len(s) for s in shards) == 8
+
+
+def test_workload_bytes_match_baseline_md():
+    """8B gate_proj 4-bit gs64 M=1 = 33,067,008 B; k_proj = 2,369,536 B;
+    70B down_proj = 132,194,304 B; per-token body bytes 8B uniform 4-bit = 3.931 GB."""
+    assert W.qmm_bytes(1, 14336, 4096, 4, 64) == 33067008
+    assert W.qmm_bytes(1, 1024, 4096, 4, 64) == 2369536
+    assert W.qmm_bytes(1, 8192, 28672, 4, 64) == 132194304
+    plan = W.layer_plan(W.MODELS["llama-3-8b"], None, 4, 64)
+    assert abs(sum(W.qmm_bytes(1, n, k, b, g) for (_, _, n, k, b, g) in plan) / 1e9 - 3.931) < 0.002
+    bp = W.stored_bpw(W.layer_plan(W.MODELS["llama-3-8b"], W.strategy_bpw40(32)))
+    assert 3.9 < bp < 4.0
+
+
+@pytest.mark.parametrize("bits,gs", [(4, 64), (2, 128), (3, 64), (6, 64), (8, 32)])
+def test_tp_shards_reassemble_and_sum(bits, gs):
+    """Column shards concatenate to the full output; row shards' partial outputs SUM to it (oracle arithmetic)."""
+    N, K, world = 32, 512, 4
+    L = packing.synth_layer(N, K, bits, gs, seed=5, with_bias=True)
+    x = A.synth_x(2, K, seed=6)
+    to_np = lambda t: t.view(torch.int16).numpy().view(np.uint16)
+    qw_np = L["qweight"].view(torch.int32).numpy().view(np.uint32)
+    full = A.quantized_matmul(x, qw_np, to_np(L["scales"]), to_np(L["zeros"]), gs, bits, "f32" if False else "bf16", "f64")
+    # column parallel
+    outs = []
+    for r in range(world):
+        sh = {k: tpmod.shard_tensor(f"model.layers.0.mlp.up_proj.{k}", L[k], bits, gs, r, world) for k in ("qweight", "scales", "zeros", "bias")}
+        assert sh["qweight"].shape == (N // world, K * bits // 32) and sh["bias"].shape == (N // world,)
+        outs.append(A.quantized_matmul(x, sh["qweight"].view(torch.int32).numpy().view(np.uint32), to_np(sh["scales"]), to_np(sh["zeros"]), gs, bits, "bf16", "f64"))
+    assert (np.concatenate(outs, axis=1) == full).all()
+    # row parallel: fp64 partials sum exactly to the fp64 truth
+    xs = A.bf16_bits_to_f32(x)
+    tot = np.zeros((2, N))
+    for r in range(world):
+        sh = {k: tpmod.shard_tensor(f"model.layers.0.mlp.down_proj.{k}", L[k], bits, gs, r, world) for k in ("qweight", "scales", "zeros", "bias")}
+        kk = K // world
+        assert sh["qweight"].shape == (N, kk * bits // 32) and sh["scales"].shape == (N, kk // gs)
+        assert (sh["bias"] == (L["bias"] if r == 0 else torch.zeros_like(L["bias"]))).all()
+        q = A.unpack_codes(sh["qweight"].view(torch.int32).numpy().view(np.uint32), bits).astype(np.float64)
+        Wd = np.repeat(A.bf16_bits_to_f32(to_np(sh["scales"])), gs, 1).astype(np.float64) * q + np.repeat(A.bf16_bits_to_f32(to_np(sh["zeros"])), gs, 1)
+        tot += xs[:, r * kk:(r + 1) * kk].astype(np.float64) @ Wd.T
+    assert np.abs(A._round_to(tot, "bf16") - full).max() == 0
+
+
+def test_tp_illegal_row_split():
+    with pytest.raises(ValueError):
+        tpmod.check_row_split(4096, 3, 64, 5)
+    with pytest.raises(ValueError):
+        tpmod.check_row_split(2048, 4, 128, 32)  # 64 codes per rank < one group of 128
+    tpmod.check_row_split(27648, 4, 128, 8)  # Qwen2.5-32B down_proj at tp8: 3456 = 27 groups -> legal
+    tpmod.check_row_split(28672, 4, 64, 8)   # Llama-3-70B down_proj at tp8: 3584 = 56 groups -> legal
