@@ -12,17 +12,17 @@
 // so one dequantised 128 x 64 weight tile feeds up to 256 tokens, and skinny batches (M = 17..64)
 // use the same kernel with a narrow N.
 //
-// Warp roles (192 threads, one CTA per SM, 4-stage ring, BLOCK_K = 64):
+// Warp roles (320 threads, one CTA per SM, 4-stage ring, BLOCK_K = 64):
 //   warp 0      TMA producer: x tile [BN tokens x 64 k] via cp.async.bulk.tensor.2d, SWIZZLE_128B,
 //               out-of-range tokens zero-filled by the TMA unit; also owns the TMEM allocation
-//   warps 1-4   dequant producers: thread r owns weight row r of the tile: loads its 64 packed codes
-//               (prefetched one k-block ahead), unpacks with (w >> s) & mask | 0x4300 (two bf16
+//   warps 1-8   dequant producers: a thread owns half a weight row of the tile per k-block: loads its 32
+//               packed codes (register ring, prefetched three k-blocks ahead), unpacks with (w >> s) & mask | 0x4300 (two bf16
 //               128+q per LOP3), applies scale*q+bias with one HFMA2.BF16 per pair (single rounding),
 //               and stores the row into the canonical K-major 128B-swizzled layout the UMMA
 //               descriptor expects (16-byte chunk c of row r at chunk position c ^ (r & 7));
 //               fence.proxy.async, then arrive.  After the main loop the same warps are the epilogue:
 //               tcgen05.ld 32x32b -> one rounding to bf16 (+ bias as a second rounded add) -> y
-//   warp 5      MMA issuer: one thread issues 4 x tcgen05.mma (K = 16) per stage and commits the
+//   warp 9      MMA issuer: one thread issues 4 x tcgen05.mma (K = 16) per stage and commits the
 //               stage's smem release and, at the end, the accumulator hand-off to the epilogue
 #include <cuda.h>
 
@@ -35,7 +35,8 @@ namespace {
 constexpr int kBlockK = 64;     // bf16 elements per k-block = one 128-byte swizzle atom
 constexpr int kTileN = 128;     // output features per CTA (= UMMA M = TMEM lanes)
 constexpr int kStages = 4;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;
+constexpr int kDequantWarps = 8;
 constexpr uint32_t kMagic = 0x43004300u;
 
 // ------------------------------------------------------------------ tcgen05 / TMA PTX wrappers
@@ -82,6 +83,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): rows of 128 bytes, 8-row
 // core groups 1024 bytes apart (SBO), LBO unused for a swizzled K-major tile one atom wide.
 __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
@@ -110,33 +121,44 @@ struct GemmParams {
     int words_per_row;
 };
 
-// 64 consecutive codes of one row (k-block kb) -> 64 bf16 weights (8 chunks of 8) = scale*q + bias
+// 32 consecutive codes of one row (half h of k-block kb) -> 32 bf16 weights (4 chunks of 8) = scale*q + bias
 template <int BITS> struct RowBlock {
-    static constexpr int NW = 2 * BITS;  // 32-bit words holding 64 codes
+    static constexpr int NW = BITS;  // 32-bit words holding 32 codes
     uint32_t w[NW];
+    uint32_t s, b;                   // raw bf16 scale / bias of the group the 32 codes belong to
 };
 
+// hb = index of the 32-code half-block along the row (= 2*kb + h)
 template <int BITS>
-__device__ __forceinline__ void load_rowblock(RowBlock<BITS>& rb, const uint32_t* __restrict__ row, int kb, bool valid) {
-    const uint32_t* src = row + (size_t)kb * RowBlock<BITS>::NW;
+__device__ __forceinline__ void load_rowblock(RowBlock<BITS>& rb, const uint32_t* __restrict__ row,
+                                              const uint16_t* __restrict__ srow, const uint16_t* __restrict__ brow, int hb,
+                                              int gs_shift, bool valid) {
+    const uint32_t* src = row + (size_t)hb * BITS;
     if (!valid) {
 #pragma unroll
-        for (int i = 0; i < RowBlock<BITS>::NW; i++) rb.w[i] = 0u;
+        for (int i = 0; i < BITS; i++) rb.w[i] = 0u;
+        rb.s = rb.b = 0u;
         return;
     }
-    if constexpr (BITS == 3) {  // 24 bytes per k-block: 8-byte aligned
+    if constexpr (BITS == 4 || BITS == 8) {
 #pragma unroll
-        for (int i = 0; i < 3; i++) {
+        for (int i = 0; i < BITS / 4; i++) {
+            const uint4 t = __ldg(reinterpret_cast<const uint4*>(src) + i);
+            rb.w[4 * i] = t.x; rb.w[4 * i + 1] = t.y; rb.w[4 * i + 2] = t.z; rb.w[4 * i + 3] = t.w;
+        }
+    } else if constexpr (BITS == 2 || BITS == 6) {
+#pragma unroll
+        for (int i = 0; i < BITS / 2; i++) {
             const uint2 t = __ldg(reinterpret_cast<const uint2*>(src) + i);
             rb.w[2 * i] = t.x; rb.w[2 * i + 1] = t.y;
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < RowBlock<BITS>::NW / 4; i++) {
-            const uint4 t = __ldg(reinterpret_cast<const uint4*>(src) + i);
-            rb.w[4 * i] = t.x; rb.w[4 * i + 1] = t.y; rb.w[4 * i + 2] = t.z; rb.w[4 * i + 3] = t.w;
-        }
+        for (int i = 0; i < BITS; i++) rb.w[i] = __ldg(src + i);
     }
+    const int g = (hb * 32) >> gs_shift;
+    rb.s = (uint32_t)__ldg(srow + g);
+    rb.b = (uint32_t)__ldg(brow + g);
 }
 
 __device__ __forceinline__ uint32_t hsub2_bf16(uint32_t a, uint32_t b) {
@@ -155,10 +177,10 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return d;
 }
 
-// chunk c (codes 8c .. 8c+7 of the k-block) as 4 packed bf16x2 registers in natural k order.
-// sraw/braw: bf16 bit patterns of the group's scale and bias.
+// chunk c (codes 8c .. 8c+7 of the 32-code half-block) as 4 packed bf16x2 registers in natural k order.
 template <int BITS>
-__device__ __forceinline__ uint4 dequant_chunk(const RowBlock<BITS>& rb, int c, uint32_t sraw, uint32_t braw) {
+__device__ __forceinline__ uint4 dequant_chunk(const RowBlock<BITS>& rb, int c) {
+    const uint32_t sraw = rb.s, braw = rb.b;
     uint4 out;
     if constexpr (BITS == 4 || BITS == 2) {
         const uint32_t s2 = sraw | (sraw << 16), b2 = braw | (braw << 16);
@@ -230,7 +252,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams p) {
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; s++) {
-            mbar_init(&full_a[s], 4);   // one arrival per dequant warp
+            mbar_init(&full_a[s], kDequantWarps);  // one arrival per dequant warp
             mbar_init(&full_b[s], 1);   // TMA producer (+ tx bytes)
             mbar_init(&empty[s], 1);    // tcgen05.commit
         }
@@ -254,7 +276,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams p) {
                 tma_load_2d(smem + (size_t)s * STAGE_BYTES + A_BYTES, &tmap_x, kb * kBlockK, m0, &full_b[s]);
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 1 + kDequantWarps) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_bf16(kTileN, BN);
@@ -277,66 +299,68 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams p) {
             umma_commit(tmem_full);      // accumulator complete -> epilogue
         }
     } else {
-        // ===================== dequant producers (warps 1-4), then epilogue =====================
+        // ===================== dequant producers (warps 1-8), then epilogue =====================
         const int q4 = warp & 3;                 // TMEM lane quarter this warp may access
+        const int h = (warp - 1) >> 2;           // which 32-code half of the k-block / which half of the columns
         const int r = q4 * 32 + lane;            // tile row == TMEM lane == output feature n0 + r
         const int64_t n = (int64_t)n0 + r;
         const bool row_ok = n < p.N;
         const uint32_t* wrow = p.w + (size_t)(row_ok ? n : 0) * p.words_per_row;
         const uint16_t* srow = p.scales + (size_t)(row_ok ? n : 0) * p.G;
         const uint16_t* brow = p.biases + (size_t)(row_ok ? n : 0) * p.G;
-        const int gpb = p.gs_shift == 5 ? 2 : 1;  // groups per k-block (group_size 32 -> 2)
 
-        RowBlock<BITS> cur, nxt;
-        uint32_t cs[2], cb[2], ns_[2], nb_[2];
-        auto load_sb = [&](int kb, uint32_t (&s)[2], uint32_t (&b)[2]) {
-            const int g0 = (kb * kBlockK) >> p.gs_shift;
-            s[0] = row_ok ? (uint32_t)__ldg(srow + g0) : 0u;
-            b[0] = row_ok ? (uint32_t)__ldg(brow + g0) : 0u;
-            if (gpb == 2) {
-                s[1] = row_ok ? (uint32_t)__ldg(srow + g0 + 1) : 0u;
-                b[1] = row_ok ? (uint32_t)__ldg(brow + g0 + 1) : 0u;
-            } else {
-                s[1] = s[0];
-                b[1] = b[0];
-            }
-        };
-        load_rowblock<BITS>(cur, wrow, 0, row_ok);
-        load_sb(0, cs, cb);
-        for (int kb = 0; kb < nkb; kb++) {
+        // register ring of packed half-blocks, fetched three k-blocks ahead (global latency ~ 3 k-blocks of MMA);
+        // the loop is unrolled by 4 so that every ring slot has a fixed register name (no copies that would
+        // wait for the loads in flight)
+        RowBlock<BITS> ring[4];
+        auto fetch = [&](int kb, RowBlock<BITS>& rb) { load_rowblock<BITS>(rb, wrow, srow, brow, 2 * kb + h, p.gs_shift, row_ok && kb < nkb); };
+        auto produce = [&](int kb, const RowBlock<BITS>& rb) {
             const int s = kb % kStages;
             const uint32_t phase = (uint32_t)(kb / kStages) & 1u;
-            if (kb + 1 < nkb) {  // prefetch the next k-block's packed words and scales
-                load_rowblock<BITS>(nxt, wrow, kb + 1, row_ok);
-                load_sb(kb + 1, ns_, nb_);
-            }
             mbar_wait(&empty[s], phase ^ 1u);
-            uint8_t* a_tile = smem + (size_t)s * STAGE_BYTES + (size_t)r * 128;
+            uint8_t* a_row = smem + (size_t)s * STAGE_BYTES + (size_t)r * 128;
 #pragma unroll
-            for (int c = 0; c < 8; c++) {
-                const int gi = (gpb == 2) ? (c >> 2) : 0;
-                const uint4 v = dequant_chunk<BITS>(cur, c, cs[gi], cb[gi]);
-                *reinterpret_cast<uint4*>(a_tile + ((c ^ (r & 7)) << 4)) = v;
+            for (int c = 0; c < 4; c++) {
+                const uint4 v = dequant_chunk<BITS>(rb, c);
+                *reinterpret_cast<uint4*>(a_row + (((4 * h + c) ^ (r & 7)) << 4)) = v;
             }
             fence_proxy_async();  // make the generic-proxy stores visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_a[s]);
-#pragma unroll
-            for (int i = 0; i < RowBlock<BITS>::NW; i++) cur.w[i] = nxt.w[i];
-            cs[0] = ns_[0]; cs[1] = ns_[1]; cb[0] = nb_[0]; cb[1] = nb_[1];
+        };
+        fetch(0, ring[0]);
+        fetch(1, ring[1]);
+        fetch(2, ring[2]);
+        for (int kb = 0; kb < nkb;) {
+            fetch(kb + 3, ring[3]);
+            produce(kb, ring[0]);
+            if (++kb >= nkb) break;
+            fetch(kb + 3, ring[0]);
+            produce(kb, ring[1]);
+            if (++kb >= nkb) break;
+            fetch(kb + 3, ring[1]);
+            produce(kb, ring[2]);
+            if (++kb >= nkb) break;
+            fetch(kb + 3, ring[2]);
+            produce(kb, ring[3]);
+            ++kb;
         }
 
-        // ---- epilogue: TMEM -> registers -> bf16 -> y[m, n]
+        // ---- epilogue: TMEM -> registers -> bf16 -> y[m, n]; warp (q4, h) drains lanes 32*q4.. and half h of the columns
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         const float bias_f = (p.bias != nullptr && row_ok) ? __bfloat162float(p.bias[n]) : 0.f;
+        constexpr int HALF = BN / 2;
+        constexpr int STEP = HALF >= 32 ? 32 : 16;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = h * HALF; c0 < (h + 1) * HALF; c0 += STEP) {
             uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c0, v);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c0;
+            if constexpr (STEP == 32) tmem_ld32(taddr, v);
+            else tmem_ld16(taddr, v);
             if (row_ok) {
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
+                for (int j = 0; j < STEP; j++) {
                     const int64_t m = (int64_t)m0 + c0 + j;
                     if (m < p.M) {
                         float f = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[j])));
