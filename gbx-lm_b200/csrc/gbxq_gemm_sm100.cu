@@ -12,17 +12,20 @@
 // so one dequantised 128 x 64 weight tile feeds up to 256 tokens, and skinny batches (M = 17..64)
 // use the same kernel with a narrow N.
 //
-// Warp roles (320 threads, one CTA per SM, 4-stage ring, BLOCK_K = 64):
-//   warp 0      TMA producer: x tile [BN tokens x 64 k] via cp.async.bulk.tensor.2d, SWIZZLE_128B,
-//               out-of-range tokens zero-filled by the TMA unit; also owns the TMEM allocation
-//   warps 1-8   dequant producers: a thread owns half a weight row of the tile per k-block: loads its 32
-//               packed codes (register ring, prefetched three k-blocks ahead), unpacks with (w >> s) & mask | 0x4300 (two bf16
+// Warp roles (576 threads, one CTA per SM, 3-4 stage ring, BLOCK_K = 64):
+//   warp 0      TMA producer (cp.async.bulk.tensor.2d): the x tile [BN tokens x 64 k] (SWIZZLE_128B,
+//               out-of-range tokens zero-filled), the PACKED weight tile [128 rows x 128 codes] for
+//               two k-blocks at a time and the tile's scales / biases [128 rows x 8 groups], each on
+//               its own mbarrier ring; also owns the TMEM allocation
+//   warps 1-16  dequant producers: a thread owns a quarter of a weight row of the tile per k-block: reads its 16
+//               packed codes and the group's scale/bias from the staging rings (no global loads, so the
+//               proxy fence below never waits on HBM), unpacks with (w >> s) & mask | 0x4300 (two bf16
 //               128+q per LOP3), applies scale*q+bias with one HFMA2.BF16 per pair (single rounding),
 //               and stores the row into the canonical K-major 128B-swizzled layout the UMMA
 //               descriptor expects (16-byte chunk c of row r at chunk position c ^ (r & 7));
 //               fence.proxy.async, then arrive.  After the main loop the same warps are the epilogue:
 //               tcgen05.ld 32x32b -> one rounding to bf16 (+ bias as a second rounded add) -> y
-//   warp 9      MMA issuer: one thread issues 4 x tcgen05.mma (K = 16) per stage and commits the
+//   warp 17     MMA issuer: one thread issues 4 x tcgen05.mma (K = 16) per stage and commits the
 //               stage's smem release and, at the end, the accumulator hand-off to the epilogue
 #include <cuda.h>
 
@@ -34,9 +37,8 @@ namespace {
 
 constexpr int kBlockK = 64;     // bf16 elements per k-block = one 128-byte swizzle atom
 constexpr int kTileN = 128;     // output features per CTA (= UMMA M = TMEM lanes)
-constexpr int kStages = 4;
-constexpr int kThreads = 320;
-constexpr int kDequantWarps = 8;
+constexpr int kDequantWarps = 16;
+constexpr int kThreads = (kDequantWarps + 2) * 32;
 constexpr uint32_t kMagic = 0x43004300u;
 
 // ------------------------------------------------------------------ tcgen05 / TMA PTX wrappers
@@ -93,6 +95,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): rows of 128 bytes, 8-row
 // core groups 1024 bytes apart (SBO), LBO unused for a swizzled K-major tile one atom wide.
 __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
@@ -110,56 +120,20 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
 }
 
 struct GemmParams {
-    const uint32_t* w;
-    const uint16_t* scales;
-    const uint16_t* biases;
     const __nv_bfloat16* bias;
     __nv_bfloat16* y;
     int64_t M, N, K;
     int gs_shift;
-    int G;
-    int words_per_row;
 };
 
-// 32 consecutive codes of one row (half h of k-block kb) -> 32 bf16 weights (4 chunks of 8) = scale*q + bias
+// The 16 (3-bit: 32) consecutive codes of one row a dequant thread owns per k-block + the raw bf16
+// scale / bias of their group.
 template <int BITS> struct RowBlock {
-    static constexpr int NW = BITS;  // 32-bit words holding 32 codes
+    static constexpr int CODES = BITS == 3 ? 32 : 16;   // 3-bit quarters are not word aligned: use halves
+    static constexpr int NW = CODES * BITS / 32;
     uint32_t w[NW];
-    uint32_t s, b;                   // raw bf16 scale / bias of the group the 32 codes belong to
+    uint32_t s, b;
 };
-
-// hb = index of the 32-code half-block along the row (= 2*kb + h)
-template <int BITS>
-__device__ __forceinline__ void load_rowblock(RowBlock<BITS>& rb, const uint32_t* __restrict__ row,
-                                              const uint16_t* __restrict__ srow, const uint16_t* __restrict__ brow, int hb,
-                                              int gs_shift, bool valid) {
-    const uint32_t* src = row + (size_t)hb * BITS;
-    if (!valid) {
-#pragma unroll
-        for (int i = 0; i < BITS; i++) rb.w[i] = 0u;
-        rb.s = rb.b = 0u;
-        return;
-    }
-    if constexpr (BITS == 4 || BITS == 8) {
-#pragma unroll
-        for (int i = 0; i < BITS / 4; i++) {
-            const uint4 t = __ldg(reinterpret_cast<const uint4*>(src) + i);
-            rb.w[4 * i] = t.x; rb.w[4 * i + 1] = t.y; rb.w[4 * i + 2] = t.z; rb.w[4 * i + 3] = t.w;
-        }
-    } else if constexpr (BITS == 2 || BITS == 6) {
-#pragma unroll
-        for (int i = 0; i < BITS / 2; i++) {
-            const uint2 t = __ldg(reinterpret_cast<const uint2*>(src) + i);
-            rb.w[2 * i] = t.x; rb.w[2 * i + 1] = t.y;
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < BITS; i++) rb.w[i] = __ldg(src + i);
-    }
-    const int g = (hb * 32) >> gs_shift;
-    rb.s = (uint32_t)__ldg(srow + g);
-    rb.b = (uint32_t)__ldg(brow + g);
-}
 
 __device__ __forceinline__ uint32_t hsub2_bf16(uint32_t a, uint32_t b) {
     uint32_t d;
@@ -177,7 +151,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return d;
 }
 
-// chunk c (codes 8c .. 8c+7 of the 32-code half-block) as 4 packed bf16x2 registers in natural k order.
+// chunk c (codes 8c .. 8c+7 of the thread's block) as 4 packed bf16x2 registers in natural k order.
 template <int BITS>
 __device__ __forceinline__ uint4 dequant_chunk(const RowBlock<BITS>& rb, int c) {
     const uint32_t sraw = rb.s, braw = rb.b;
@@ -190,22 +164,18 @@ __device__ __forceinline__ uint4 dequant_chunk(const RowBlock<BITS>& rb, int c) 
 #pragma unroll
             for (int i = 0; i < 4; i++)  // (nibble i, nibble i+4)
                 pr[i] = hsub2_bf16(lop3_and_or(word >> (4 * i), 0x000f000fu, kMagic), kMagic);
-            // re-pair (0,4),(1,5),(2,6),(3,7) -> (0,1),(2,3),(4,5),(6,7)
-            const uint32_t q01 = __byte_perm(pr[0], pr[1], 0x5410), q45 = __byte_perm(pr[0], pr[1], 0x7632);
-            const uint32_t q23 = __byte_perm(pr[2], pr[3], 0x5410), q67 = __byte_perm(pr[2], pr[3], 0x7632);
-            out.x = hfma2_bf16(q01, s2, b2); out.y = hfma2_bf16(q23, s2, b2);
-            out.z = hfma2_bf16(q45, s2, b2); out.w = hfma2_bf16(q67, s2, b2);
         } else {
-            // 2-bit: word holds 16 codes; chunk c uses fields 8*(c&1) .. +7 of word c>>1
-            const uint32_t half = rb.w[c >> 1] >> (16 * (c & 1));  // fields f .. f+7 now at bits 0..15
+            // 2-bit: a word holds 16 codes; chunk c = fields 8*(c&1) .. +7 of word c>>1
+            const uint32_t half = rb.w[c >> 1] >> (16 * (c & 1));  // the chunk's 8 fields now at bits 0..15
 #pragma unroll
-            for (int i = 0; i < 4; i++)  // (field i, field i+4) of the 8: bits 2i and 2i+8
+            for (int i = 0; i < 4; i++)  // (field i, field i+4): bits 2i and 2i+8 -> low bits of each half
                 pr[i] = hsub2_bf16(lop3_and_or(__byte_perm(half >> (2 * i), 0u, 0x4140), 0x00030003u, kMagic), kMagic);
-            const uint32_t q01 = __byte_perm(pr[0], pr[1], 0x5410), q45 = __byte_perm(pr[0], pr[1], 0x7632);
-            const uint32_t q23 = __byte_perm(pr[2], pr[3], 0x5410), q67 = __byte_perm(pr[2], pr[3], 0x7632);
-            out.x = hfma2_bf16(q01, s2, b2); out.y = hfma2_bf16(q23, s2, b2);
-            out.z = hfma2_bf16(q45, s2, b2); out.w = hfma2_bf16(q67, s2, b2);
         }
+        // re-pair (0,4),(1,5),(2,6),(3,7) -> (0,1),(2,3),(4,5),(6,7)
+        const uint32_t q01 = __byte_perm(pr[0], pr[1], 0x5410), q45 = __byte_perm(pr[0], pr[1], 0x7632);
+        const uint32_t q23 = __byte_perm(pr[2], pr[3], 0x5410), q67 = __byte_perm(pr[2], pr[3], 0x7632);
+        out.x = hfma2_bf16(q01, s2, b2); out.y = hfma2_bf16(q23, s2, b2);
+        out.z = hfma2_bf16(q45, s2, b2); out.w = hfma2_bf16(q67, s2, b2);
     } else {
         // generic widths (3, 6, 8): exact small integers via the fp32 magic number, fp32 FMA, one rounding
         const float s = __uint_as_float(sraw << 16), b = __uint_as_float(braw << 16);
@@ -226,21 +196,47 @@ __device__ __forceinline__ uint4 dequant_chunk(const RowBlock<BITS>& rb, int c) 
     return out;
 }
 
+template <int BITS, int BN> struct Cfg {
+    // Two rings decoupled by depth: the x tiles (TMA, ~1 us latency) run 4-6 k-blocks ahead of the MMA,
+    // the dequantised weight tiles (produced on-chip) only 3.
+    static constexpr int XSTAGES = BN == 256 ? 4 : 6;
+    static constexpr int ASTAGES = 3;
+    static constexpr uint32_t A_BYTES = kTileN * kBlockK * 2;          // 16 KB
+    static constexpr uint32_t B_BYTES = BN * kBlockK * 2;
+    static constexpr uint32_t W_ROW_BYTES = 16 * BITS;                 // packed bytes of 128 codes (2 k-blocks)
+    static constexpr uint32_t W_SLOT = kTileN * W_ROW_BYTES;           // 2*BITS KB
+    static constexpr int W_SLOTS = (32 * 1024 / W_SLOT) >= 4 ? 4 : 2;  // packed-weight ring (pairs of k-blocks)
+    static constexpr uint32_t S_SLOT = 2 * kTileN * 16;                // scales + biases, 8 groups per row
+    static constexpr int S_SLOTS = 2;
+    static constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    static constexpr size_t SMEM = (size_t)XSTAGES * B_BYTES + (size_t)ASTAGES * A_BYTES + (size_t)W_SLOTS * W_SLOT +
+                                   (size_t)S_SLOTS * S_SLOT + (2 * XSTAGES + 2 * ASTAGES + 2 * W_SLOTS + 2 * S_SLOTS + 1) * 8 +
+                                   16 + 1024;
+};
+
 template <int BITS, int BN>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams p) {
-    constexpr uint32_t A_BYTES = kTileN * kBlockK * 2;  // 16 KB
-    constexpr uint32_t B_BYTES = BN * kBlockK * 2;
-    constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+            const __grid_constant__ CUtensorMap tmap_s, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+    using C = Cfg<BITS, BN>;
+    constexpr int XS = C::XSTAGES, AS = C::ASTAGES, WS = C::W_SLOTS, SS = C::S_SLOTS;
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment for the 128B-swizzled tiles
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full_a = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * STAGE_BYTES);
-    uint64_t* full_b = full_a + kStages;
-    uint64_t* empty = full_b + kStages;
-    uint64_t* tmem_full = empty + kStages;
+    uint8_t* xring = smem;                                   // [XS][BN x 64] bf16, 128B-swizzled (TMA)
+    uint8_t* aring = xring + (size_t)XS * C::B_BYTES;        // [AS][128 x 64] bf16, 128B-swizzled (dequant warps)
+    uint8_t* wring = aring + (size_t)AS * C::A_BYTES;
+    uint8_t* sring = wring + (size_t)WS * C::W_SLOT;
+    uint64_t* full_a = reinterpret_cast<uint64_t*>(sring + (size_t)SS * C::S_SLOT);
+    uint64_t* empty_a = full_a + AS;
+    uint64_t* full_b = empty_a + AS;
+    uint64_t* empty_b = full_b + XS;
+    uint64_t* wfull = empty_b + XS;
+    uint64_t* wempty = wfull + WS;
+    uint64_t* sfull = wempty + WS;
+    uint64_t* sempty = sfull + SS;
+    uint64_t* tmem_full = sempty + SS;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5;
@@ -248,32 +244,66 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams p) {
     const int n0 = blockIdx.x * kTileN;
     const int m0 = blockIdx.y * BN;
     const int nkb = (int)(p.K / kBlockK);
+    const int npair = (nkb + 1) >> 1;                     // packed-weight slots: 2 k-blocks each
+    const int kb_per_s = p.gs_shift == 5 ? 4 : (p.gs_shift == 6 ? 8 : 16);  // k-blocks per scale slot (8 groups)
+    const int nsl = (nkb + kb_per_s - 1) / kb_per_s;
 
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < kStages; s++) {
+        for (int s = 0; s < AS; s++) {
             mbar_init(&full_a[s], kDequantWarps);  // one arrival per dequant warp
-            mbar_init(&full_b[s], 1);   // TMA producer (+ tx bytes)
-            mbar_init(&empty[s], 1);    // tcgen05.commit
+            mbar_init(&empty_a[s], 1);             // tcgen05.commit
+        }
+#pragma unroll
+        for (int s = 0; s < XS; s++) {
+            mbar_init(&full_b[s], 1);              // TMA producer (+ tx bytes)
+            mbar_init(&empty_b[s], 1);             // tcgen05.commit
+        }
+#pragma unroll
+        for (int s = 0; s < WS; s++) {
+            mbar_init(&wfull[s], 1);
+            mbar_init(&wempty[s], kDequantWarps);
+        }
+#pragma unroll
+        for (int s = 0; s < SS; s++) {
+            mbar_init(&sfull[s], 1);
+            mbar_init(&sempty[s], kDequantWarps);
         }
         mbar_init(tmem_full, 1);
         fence_mbar_init();
     }
-    if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == 0) tmem_alloc(tmem_slot, C::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer (x tile) =====================
+        // ===================== TMA producer =====================
         if (lane == 0) {
+            auto issue_w = [&](int pr) {  // packed weights of k-blocks 2pr, 2pr+1
+                const int s = pr % WS;
+                mbar_wait(&wempty[s], ((uint32_t)(pr / WS) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(&wfull[s], C::W_SLOT);
+                tma_load_2d(wring + (size_t)s * C::W_SLOT, &tmap_w, pr * 4 * BITS, n0, &wfull[s]);
+            };
+            auto issue_s = [&](int sl) {  // scales + biases of groups 8sl .. 8sl+7
+                const int s = sl % SS;
+                mbar_wait(&sempty[s], ((uint32_t)(sl / SS) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(&sfull[s], C::S_SLOT);
+                tma_load_2d(sring + (size_t)s * C::S_SLOT, &tmap_s, sl * 8, n0, &sfull[s]);
+                tma_load_2d(sring + (size_t)s * C::S_SLOT + kTileN * 16, &tmap_b, sl * 8, n0, &sfull[s]);
+            };
+            // run the small streams ahead of the x stream: WS-1 weight slots and one scale slot in flight
+            issue_s(0);
+            for (int pr = 0; pr < WS - 1 && pr < npair; pr++) issue_w(pr);
             for (int kb = 0; kb < nkb; kb++) {
-                const int s = kb % kStages;
-                const uint32_t phase = (uint32_t)(kb / kStages) & 1u;
-                mbar_wait(&empty[s], phase ^ 1u);
-                mbar_arrive_expect_tx(&full_b[s], B_BYTES);
-                tma_load_2d(smem + (size_t)s * STAGE_BYTES + A_BYTES, &tmap_x, kb * kBlockK, m0, &full_b[s]);
+                if ((kb & 1) == 0 && (kb >> 1) + WS - 1 < npair) issue_w((kb >> 1) + WS - 1);
+                if (kb % kb_per_s == 0 && kb / kb_per_s + 1 < nsl) issue_s(kb / kb_per_s + 1);
+                const int s = kb % XS;
+                mbar_wait(&empty_b[s], ((uint32_t)(kb / XS) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(&full_b[s], C::B_BYTES);
+                tma_load_2d(xring + (size_t)s * C::B_BYTES, &tmap_x, kb * kBlockK, m0, &full_b[s]);
             }
         }
     } else if (warp == 1 + kDequantWarps) {
@@ -281,83 +311,96 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams p) {
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_bf16(kTileN, BN);
             for (int kb = 0; kb < nkb; kb++) {
-                const int s = kb % kStages;
-                const uint32_t phase = (uint32_t)(kb / kStages) & 1u;
-                mbar_wait(&full_a[s], phase);
-                mbar_wait(&full_b[s], phase);
+                const int sa = kb % AS, sx = kb % XS;
+                mbar_wait(&full_a[sa], (uint32_t)(kb / AS) & 1u);
+                mbar_wait(&full_b[sx], (uint32_t)(kb / XS) & 1u);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + (size_t)s * STAGE_BYTES);
-                const uint32_t b_addr = a_addr + A_BYTES;
+                const uint32_t a_addr = smem_u32(aring + (size_t)sa * C::A_BYTES);
+                const uint32_t b_addr = smem_u32(xring + (size_t)sx * C::B_BYTES);
 #pragma unroll
                 for (int k = 0; k < kBlockK / 16; k++) {
                     const uint64_t ad = make_sw128_kmajor_desc(a_addr + k * 32);
                     const uint64_t bd = make_sw128_kmajor_desc(b_addr + k * 32);
                     umma_f16(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
                 }
-                umma_commit(&empty[s]);  // frees the smem stage when these MMAs retire
+                umma_commit(&empty_a[sa]);  // both ring slots are free once these MMAs retire
+                umma_commit(&empty_b[sx]);
             }
             umma_commit(tmem_full);      // accumulator complete -> epilogue
         }
     } else {
-        // ===================== dequant producers (warps 1-8), then epilogue =====================
-        const int q4 = warp & 3;                 // TMEM lane quarter this warp may access
-        const int h = (warp - 1) >> 2;           // which 32-code half of the k-block / which half of the columns
-        const int r = q4 * 32 + lane;            // tile row == TMEM lane == output feature n0 + r
-        const int64_t n = (int64_t)n0 + r;
-        const bool row_ok = n < p.N;
-        const uint32_t* wrow = p.w + (size_t)(row_ok ? n : 0) * p.words_per_row;
-        const uint16_t* srow = p.scales + (size_t)(row_ok ? n : 0) * p.G;
-        const uint16_t* brow = p.biases + (size_t)(row_ok ? n : 0) * p.G;
+        // ===================== dequant producers (warps 1-16), then epilogue =====================
+        const int dw = warp - 1;                 // 0..15
+        const int r = dw * 8 + (lane >> 2);      // tile row this thread dequantises
+        const int qk = lane & 3;                 // which 16-code quarter of the k-block
+        using RB = RowBlock<BITS>;
+        constexpr int CPT = RB::CODES / 8;       // 16-byte chunks this thread writes per k-block
+        const bool lane_on = (BITS != 3) || ((qk & 1) == 0);
+        const int c_base = (BITS == 3) ? (qk >> 1) * 4 : qk * 2;   // first chunk (of 8) this thread writes
+        const uint32_t wring_u32 = smem_u32(wring), sring_u32 = smem_u32(sring);
 
-        // register ring of packed half-blocks, fetched three k-blocks ahead (global latency ~ 3 k-blocks of MMA);
-        // the loop is unrolled by 4 so that every ring slot has a fixed register name (no copies that would
-        // wait for the loads in flight)
-        RowBlock<BITS> ring[4];
-        auto fetch = [&](int kb, RowBlock<BITS>& rb) { load_rowblock<BITS>(rb, wrow, srow, brow, 2 * kb + h, p.gs_shift, row_ok && kb < nkb); };
-        auto produce = [&](int kb, const RowBlock<BITS>& rb) {
-            const int s = kb % kStages;
-            const uint32_t phase = (uint32_t)(kb / kStages) & 1u;
-            mbar_wait(&empty[s], phase ^ 1u);
-            uint8_t* a_row = smem + (size_t)s * STAGE_BYTES + (size_t)r * 128;
+        for (int kb = 0; kb < nkb; kb++) {
+            const int pr = kb >> 1, ws = pr % WS;
+            const int sl = kb / kb_per_s, ss = sl % SS;
+            if ((kb & 1) == 0) mbar_wait(&wfull[ws], (uint32_t)(pr / WS) & 1u);
+            if (kb % kb_per_s == 0) mbar_wait(&sfull[ss], (uint32_t)(sl / SS) & 1u);
+            // ---- this thread's packed codes and their group's scale / bias, from the staging rings
+            RB rb;
+            if (lane_on) {
+                const uint32_t wa = wring_u32 + (uint32_t)ws * C::W_SLOT + (uint32_t)r * C::W_ROW_BYTES +
+                                    (uint32_t)((kb & 1) * 8 * BITS) + (uint32_t)(c_base * BITS);  // c_base*8 codes*BITS/8 bytes
+                if constexpr (RB::NW == 4) {
+                    const uint4 t = lds128(wa);
+                    rb.w[0] = t.x; rb.w[1] = t.y; rb.w[2] = t.z; rb.w[3] = t.w;
+                } else if constexpr (RB::NW == 2) {
+                    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(rb.w[0]), "=r"(rb.w[1]) : "r"(wa));
+                } else {
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const uint4 v = dequant_chunk<BITS>(rb, c);
-                *reinterpret_cast<uint4*>(a_row + (((4 * h + c) ^ (r & 7)) << 4)) = v;
+                    for (int i = 0; i < RB::NW; i++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rb.w[i]) : "r"(wa + 4 * i));
+                }
+                const int gl = ((kb * kBlockK + c_base * 8) >> p.gs_shift) & 7;  // group inside the 8-group slot
+                const uint32_t sa = sring_u32 + (uint32_t)ss * C::S_SLOT + (uint32_t)r * 16 + (uint32_t)gl * 2;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(rb.s) : "r"(sa));
+                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(rb.b) : "r"(sa + kTileN * 16));
+            }
+            const int s = kb % AS;
+            mbar_wait(&empty_a[s], ((uint32_t)(kb / AS) & 1u) ^ 1u);
+            if (lane_on) {
+                uint8_t* a_row = aring + (size_t)s * C::A_BYTES + (size_t)r * 128;
+#pragma unroll
+                for (int c = 0; c < CPT; c++) {
+                    const uint4 v = dequant_chunk<BITS>(rb, c);
+                    *reinterpret_cast<uint4*>(a_row + (((c_base + c) ^ (r & 7)) << 4)) = v;
+                }
             }
             fence_proxy_async();  // make the generic-proxy stores visible to the tensor core (async proxy)
             __syncwarp();
-            if (lane == 0) mbar_arrive(&full_a[s]);
-        };
-        fetch(0, ring[0]);
-        fetch(1, ring[1]);
-        fetch(2, ring[2]);
-        for (int kb = 0; kb < nkb;) {
-            fetch(kb + 3, ring[3]);
-            produce(kb, ring[0]);
-            if (++kb >= nkb) break;
-            fetch(kb + 3, ring[0]);
-            produce(kb, ring[1]);
-            if (++kb >= nkb) break;
-            fetch(kb + 3, ring[1]);
-            produce(kb, ring[2]);
-            if (++kb >= nkb) break;
-            fetch(kb + 3, ring[2]);
-            produce(kb, ring[3]);
-            ++kb;
+            if (lane == 0) {
+                mbar_arrive(&full_a[s]);
+                if ((kb & 1) == 1 || kb == nkb - 1) mbar_arrive(&wempty[ws]);
+                if (kb % kb_per_s == kb_per_s - 1 || kb == nkb - 1) mbar_arrive(&sempty[ss]);
+            }
         }
 
-        // ---- epilogue: TMEM -> registers -> bf16 -> y[m, n]; warp (q4, h) drains lanes 32*q4.. and half h of the columns
+        // ---- epilogue: TMEM -> registers -> bf16 -> y[m, n]; warp drains TMEM lanes 32*(warp%4).. (its hardware
+        //      quarter) and column quarter (dw >> 2) of the accumulator
         mbar_wait(tmem_full, 0);
         tc_fence_after();
+        const int q4 = warp & 3;
+        const int er = q4 * 32 + lane;
+        const int64_t n = (int64_t)n0 + er;
+        const bool row_ok = n < p.N;
         const float bias_f = (p.bias != nullptr && row_ok) ? __bfloat162float(p.bias[n]) : 0.f;
-        constexpr int HALF = BN / 2;
-        constexpr int STEP = HALF >= 32 ? 32 : 16;
+        constexpr int QCOLS = BN / 4;
+        constexpr int STEP = QCOLS >= 32 ? 32 : (QCOLS >= 16 ? 16 : 8);
+        const int cq = dw >> 2;
 #pragma unroll 1
-        for (int c0 = h * HALF; c0 < (h + 1) * HALF; c0 += STEP) {
+        for (int c0 = cq * QCOLS; c0 < (cq + 1) * QCOLS; c0 += STEP) {
             uint32_t v[32];
             const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c0;
             if constexpr (STEP == 32) tmem_ld32(taddr, v);
-            else tmem_ld16(taddr, v);
+            else if constexpr (STEP == 16) tmem_ld16(taddr, v);
+            else tmem_ld8(taddr, v);
             if (row_ok) {
 #pragma unroll
                 for (int j = 0; j < STEP; j++) {
@@ -375,7 +418,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams p) {
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
     }
 }
 
@@ -398,9 +441,26 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
+bool encode_2d(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+               uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle sw) {
+    EncodeTiledFn enc = get_encode();
+    if (enc == nullptr) return false;
+    const cuuint64_t gdim[2] = {inner, outer};
+    const cuuint64_t gstride[1] = {pitch_bytes};
+    const cuuint32_t box[2] = {box_inner, box_outer};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(tm, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct Maps {
+    CUtensorMap x, w, s, b;
+};
+
 template <int BITS, int BN>
-int launch_inst(const CUtensorMap& tmap, const GemmParams& p, cudaStream_t st) {
-    constexpr size_t smem = (size_t)kStages * (kTileN * kBlockK * 2 + BN * kBlockK * 2) + 1024 + 256;
+int launch_inst(const Maps& mp, const GemmParams& p, cudaStream_t st) {
+    constexpr size_t smem = Cfg<BITS, BN>::SMEM;
+    static_assert(smem <= 227 * 1024, "shared memory budget");
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BITS, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -408,18 +468,18 @@ int launch_inst(const CUtensorMap& tmap, const GemmParams& p, cudaStream_t st) {
         configured = true;
     }
     dim3 grid((unsigned)((p.N + kTileN - 1) / kTileN), (unsigned)((p.M + BN - 1) / BN));
-    gemm_kernel<BITS, BN><<<grid, kThreads, smem, st>>>(tmap, p);
+    gemm_kernel<BITS, BN><<<grid, kThreads, smem, st>>>(mp.x, mp.w, mp.s, mp.b, p);
     count_launch();
     return check_cuda(cudaGetLastError());
 }
 
 template <int BITS>
-int launch_bn(int bn, const CUtensorMap& tmap, const GemmParams& p, cudaStream_t st) {
+int launch_bn(int bn, const Maps& mp, const GemmParams& p, cudaStream_t st) {
     switch (bn) {
-        case 32: return launch_inst<BITS, 32>(tmap, p, st);
-        case 64: return launch_inst<BITS, 64>(tmap, p, st);
-        case 128: return launch_inst<BITS, 128>(tmap, p, st);
-        default: return launch_inst<BITS, 256>(tmap, p, st);
+        case 32: return launch_inst<BITS, 32>(mp, p, st);
+        case 64: return launch_inst<BITS, 64>(mp, p, st);
+        case 128: return launch_inst<BITS, 128>(mp, p, st);
+        default: return launch_inst<BITS, 256>(mp, p, st);
     }
 }
 
@@ -429,10 +489,10 @@ int pick_bn(int64_t M) { return M <= 32 ? 32 : (M <= 64 ? 64 : (M <= 128 ? 128 :
 
 bool gemm_supported(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype, const void* x, const void* w,
                     const void* y) {
-    (void)gs;
-    (void)bits;
     if (dtype != GBXQ_BF16 || M < 1 || N < 1) return false;
     if (K % kBlockK) return false;
+    if ((K * bits / 8) % 16) return false;      // TMA: packed row pitch must be a multiple of 16 bytes
+    if (((K / gs) * 2) % 16) return false;      // TMA: scale row pitch must be a multiple of 16 bytes
     if (((uintptr_t)x | (uintptr_t)w) & 15) return false;
     if ((uintptr_t)y & 1) return false;
     if (M > (int64_t)1 << 24 || (N + kTileN - 1) / kTileN > 65535 * 32) return false;
@@ -441,37 +501,32 @@ bool gemm_supported(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype
 
 int launch_gemm(const void* x, const uint32_t* w, const void* s, const void* b, const void* bias, void* y, int64_t M,
                 int64_t N, int64_t K, int bits, int gs, cudaStream_t st) {
-    EncodeTiledFn enc = get_encode();
-    if (enc == nullptr) return GBXQ_EUNSUPPORTED;
+    if (get_encode() == nullptr) return GBXQ_EUNSUPPORTED;
+    if (((uintptr_t)s | (uintptr_t)b) & 15) return GBXQ_EUNSUPPORTED;
     const int bn = pick_bn(M);
     if ((M + bn - 1) / bn > 65535) return GBXQ_EUNSUPPORTED;
-    CUtensorMap tmap;
-    const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)M};
-    const cuuint64_t gstride[1] = {(cuuint64_t)K * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)bn};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(x), gdim, gstride, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (cr != CUDA_SUCCESS) return GBXQ_EUNSUPPORTED;
+    Maps mp;
+    const uint64_t words = (uint64_t)(K * bits / 32), G = (uint64_t)(K / gs);
+    bool ok = encode_2d(&mp.x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, x, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, kBlockK, (uint32_t)bn,
+                        CU_TENSOR_MAP_SWIZZLE_128B);
+    ok = ok && encode_2d(&mp.w, CU_TENSOR_MAP_DATA_TYPE_UINT32, w, words, (uint64_t)N, words * 4, (uint32_t)(4 * bits), kTileN,
+                         CU_TENSOR_MAP_SWIZZLE_NONE);
+    ok = ok && encode_2d(&mp.s, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, s, G, (uint64_t)N, G * 2, 8, kTileN, CU_TENSOR_MAP_SWIZZLE_NONE);
+    ok = ok && encode_2d(&mp.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, b, G, (uint64_t)N, G * 2, 8, kTileN, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (!ok) return GBXQ_EUNSUPPORTED;
     GemmParams p{};
-    p.w = w;
-    p.scales = reinterpret_cast<const uint16_t*>(s);
-    p.biases = reinterpret_cast<const uint16_t*>(b);
     p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
     p.y = reinterpret_cast<__nv_bfloat16*>(y);
     p.M = M;
     p.N = N;
     p.K = K;
     p.gs_shift = gs == 32 ? 5 : (gs == 64 ? 6 : 7);
-    p.G = (int)(K / gs);
-    p.words_per_row = (int)(K * bits / 32);
     switch (bits) {
-        case 2: return launch_bn<2>(bn, tmap, p, st);
-        case 3: return launch_bn<3>(bn, tmap, p, st);
-        case 4: return launch_bn<4>(bn, tmap, p, st);
-        case 6: return launch_bn<6>(bn, tmap, p, st);
-        case 8: return launch_bn<8>(bn, tmap, p, st);
+        case 2: return launch_bn<2>(bn, mp, p, st);
+        case 3: return launch_bn<3>(bn, mp, p, st);
+        case 4: return launch_bn<4>(bn, mp, p, st);
+        case 6: return launch_bn<6>(bn, mp, p, st);
+        case 8: return launch_bn<8>(bn, mp, p, st);
     }
     return GBXQ_EINVAL_BITS;
 }

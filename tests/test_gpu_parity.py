@@ -132,8 +132,18 @@ def test_qmm_gemm_tcgen05_vs_oracle(cuda_device, bits, gs):
     """tcgen05/TMEM GEMM with in-kernel dequant: the weight operand is rounded once to bf16
     (RN(scale*q+bias)), accumulation is fp32 in TMEM; tolerance = the path's 1e-2 (north_star)."""
     g = _ops()
-    for (M, N, K) in ((17, 128, 256), (64, 200, 512), (100, 384, 1024), (300, 130, 2048)):
+    # the TMA descriptors need 16-byte row pitches: K*bits/8 and (K/gs)*2 multiples of 16
+    for (M, N, K) in ((17, 128, 1024), (64, 200, 1024), (100, 384, 2048), (300, 130, 4096)):
         _run_case(g, cuda_device, "gemm", bits, gs, M, N, K, seed=bits + gs + M, with_bias=(M == 100), tol=1e-2)
+
+
+def test_qmm_gemm_declines_unaligned_pitch(cuda_device):
+    """K = 256 with gs = 128 gives a 4-byte scale row pitch: the forced tensor-core kernel refuses
+    (no silent fallback), auto dispatch serves the call with another kernel."""
+    g = _ops()
+    with pytest.raises(RuntimeError):
+        _run_case(g, cuda_device, "gemm", 4, 128, 20, 64, 256, seed=1)
+    _run_case(g, cuda_device, "auto", 4, 128, 20, 64, 256, seed=1, tol=1e-2)
 
 
 def test_qmm_gemm_prefill_shape_properties(cuda_device):
