@@ -169,4 +169,10 @@ int launch_allreduce_oneshot(const void* in, void* out, int64_t count, int dtype
 
 int device_sm_count();
 
+// Host: encode a 2-D tiled TMA descriptor (dtype 0 = bf16, 1 = uint32) through the driver entry point obtained with
+// cudaGetDriverEntryPoint (no libcuda link).  `tm` points at a CUtensorMap.  Returns false if unavailable.
+bool tma_encode_available();
+bool encode_tensor_map_2d(void* tm, int dtype, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                          uint32_t box_inner, uint32_t box_outer, bool swizzle128);
+
 }  // namespace gbxq

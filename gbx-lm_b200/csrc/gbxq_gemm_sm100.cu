@@ -487,6 +487,15 @@ int pick_bn(int64_t M) { return M <= 32 ? 32 : (M <= 64 ? 64 : (M <= 128 ? 128 :
 
 }  // namespace
 
+bool tma_encode_available() { return get_encode() != nullptr; }
+
+bool encode_tensor_map_2d(void* tm, int dtype, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                          uint32_t box_inner, uint32_t box_outer, bool swizzle128) {
+    return encode_2d(reinterpret_cast<CUtensorMap*>(tm), dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT32,
+                     base, inner, outer, pitch_bytes, box_inner, box_outer,
+                     swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+
 bool gemm_supported(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype, const void* x, const void* w,
                     const void* y) {
     if (dtype != GBXQ_BF16 || M < 1 || N < 1) return false;

@@ -12,9 +12,11 @@
 //
 //   * Work split: a CTA owns a contiguous range of weight rows (balanced at single-row granularity).
 //     It walks row-blocks (<= 64 rows) x k-tiles (16 quantisation groups, one per consumer warp).
-//     Stage = (row-block, k-tile): a producer warp issues one `cp.async.bulk` (TMA engine, SASS
-//     UBLKCP) per row into a 4-deep shared-memory ring with a padded row pitch (conflict-free
-//     fragment loads), completion counted in bytes on an mbarrier.
+//     Stage = (row-block, k-tile): the producer issues one 2-D TMA box [rows x 128 B] per 128 bytes of
+//     row piece (cp.async.bulk.tensor.2d, SWIZZLE_128B so that the fragment loads of 8 different rows
+//     hit different banks) into a 4-deep shared-memory ring, completion counted in bytes on an
+//     mbarrier.  (Per-row 1-D bulk copies were measured at ~85 cycles per request -- 6 B/clk/SM --
+//     which is why the tile goes through tensor maps.)
 //   * Consumer warp w owns group (16*kt + w): thread (g, t) of the warp holds the t-th quarter of
 //     the group's codes of rows g and g+8 -- exactly the m16n8k16 A fragment.  The k order inside a
 //     group is free, so the pair one LOP3 extracts ((w >> s) & mask | 0x4300 = two bf16 values
@@ -23,10 +25,14 @@
 //     product sits alone in the accumulator and is folded as
 //         y += scale * D + (bias - OFF*scale) * sum(x over the group)
 //     in fp32 (OFF = 128 carried by the bf16 images of the codes; 256 for the two 8-bit images).
-//   * x B-fragments and the (scale, bias) pairs are prefetched one stage ahead from L2 into
-//     registers; the 16 per-warp partial sums of a row-block meet in shared memory and are added in
+//   * the stage's scales and biases ride the same ring (one 2-D TMA box [rows x 16 groups] each), the x
+//     B-fragments are prefetched one stage ahead from L2 into registers, and sum(x) per group comes
+//     out of one extra MMA against an all-ones A fragment; the 16 per-warp partial sums of a row-block meet in shared memory and are added in
 //     fixed order (bitwise reproducible), rounded once to bf16 (+ optional bias as a second rounded
 //     add) and stored coalesced.
+#include <cuda.h>
+#include <string.h>
+
 #include "gbxq_common.cuh"
 
 namespace gbxq {
@@ -70,13 +76,25 @@ struct SkinnyParams {
     int n_kt;         // k-tiles (16 groups each)
     int rs;           // rows per stage (multiple of 16, <= kMaxRS)
     uint32_t row_bytes;
-    uint32_t piece_bytes;  // bytes of one row inside a full k-tile (16 groups)
-    uint32_t pitch;        // shared-memory row pitch (piece_bytes + pad)
+    uint32_t piece_words;  // 32-bit words of one row inside a full k-tile (16 groups)
+    int nbox;              // 128-byte-wide TMA boxes per row piece
+    uint32_t sb_off;       // offset of the scale box inside a ring slot (bias box follows at + rs*32)
+    uint32_t slot_bytes;
 };
 
+__device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+
 // BITS in {2,4,8}; QW = 32-bit words per thread-quarter of a group (= group_size * BITS / 128)
-template <int BITS, int QW>
-__global__ void __launch_bounds__(kThreads, 1) skinny_kernel(const SkinnyParams p) {
+template <int BITS, int QW, bool SB_TMA>
+__global__ void __launch_bounds__(kThreads, 1)
+skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_s,
+              const __grid_constant__ CUtensorMap tmap_b, const SkinnyParams p) {
     constexpr int CQ = QW * 32 / BITS;       // codes per quarter
     constexpr int P = CQ / 2;                // pairs (= A/B registers) per quarter
     constexpr int S = P / 2;                 // MMA k16 steps per group
@@ -85,9 +103,11 @@ __global__ void __launch_bounds__(kThreads, 1) skinny_kernel(const SkinnyParams 
     constexpr float OFF = BITS == 8 ? 256.f : 128.f;
     static_assert(S >= 1 && (QW == 1 || QW == 2 || QW == 4 || QW == 8), "unsupported quarter");
 
-    extern __shared__ __align__(1024) uint8_t smem[];
-    // layout: [ring kStages * rs * pitch][barriers][red kWarps * rs * 8 f32]
-    const uint32_t slot_bytes = (uint32_t)p.rs * p.pitch;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // layout: [ring kStages * slot][barriers][red kWarps * rs * 8 f32]; slot = [nbox boxes of rs rows x 128 B,
+    // 128B-swizzled][scales rs x 16 bf16][biases rs x 16 bf16]
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t slot_bytes = p.slot_bytes;
     uint8_t* ring = smem;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + (size_t)kStages * slot_bytes);
     uint64_t* empty_bar = full_bar + kStages;
@@ -116,22 +136,25 @@ __global__ void __launch_bounds__(kThreads, 1) skinny_kernel(const SkinnyParams 
     __syncthreads();
 
     if (warp == kWarps) {
-        // ===================== producer warp: one bulk copy per row of the stage =====================
-        for (int it = 0; it < ns; it++) {
-            const int s = it % kStages;
-            const uint32_t phase = (uint32_t)(it / kStages) & 1u;
-            const int rb = it / p.n_kt, kt = it - rb * p.n_kt;
-            const int ra = rb * rb_rows;
-            int nr = rows - ra;
-            if (nr > rb_rows) nr = rb_rows;
-            uint32_t pb = p.row_bytes - (uint32_t)kt * p.piece_bytes;
-            if (pb > p.piece_bytes) pb = p.piece_bytes;
-            mbar_wait(&empty_bar[s], phase ^ 1u);
-            if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)nr * pb);
-            __syncwarp();
-            const uint8_t* src = p.w + (uint64_t)(r0 + ra) * p.row_bytes + (uint64_t)kt * p.piece_bytes;
-            uint8_t* dst = ring + (size_t)s * slot_bytes;
-            for (int i = lane; i < nr; i += 32) bulk_g2s(dst + (size_t)i * p.pitch, src + (uint64_t)i * p.row_bytes, pb, &full_bar[s]);
+        // ===================== producer: a handful of TMA boxes per stage =====================
+        if (lane == 0) {
+            const uint32_t box_bytes = (uint32_t)p.rs * 128u;
+            for (int it = 0; it < ns; it++) {
+                const int s = it % kStages;
+                const uint32_t phase = (uint32_t)(it / kStages) & 1u;
+                const int rb = it / p.n_kt, kt = it - rb * p.n_kt;
+                const int row = (int)(r0 + rb * rb_rows);
+                mbar_wait(&empty_bar[s], phase ^ 1u);
+                uint8_t* dst = ring + (size_t)s * slot_bytes;
+                // boxes always count full bytes: rows past N and words past the row end are zero-filled by the TMA unit
+                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.nbox * box_bytes + (SB_TMA ? 2u * (uint32_t)p.rs * 32u : 0u));
+                for (int b = 0; b < p.nbox; b++)
+                    tma_load_2d(dst + (size_t)b * box_bytes, &tmap_w, kt * (int)p.piece_words + b * 32, row, &full_bar[s]);
+                if constexpr (SB_TMA) {
+                    tma_load_2d(dst + p.sb_off, &tmap_s, kt * kWarps, row, &full_bar[s]);
+                    tma_load_2d(dst + p.sb_off + (uint32_t)p.rs * 32u, &tmap_b, kt * kWarps, row, &full_bar[s]);
+                }
+            }
         }
     } else {
         // ===================== consumer warps =====================
@@ -159,15 +182,17 @@ __global__ void __launch_bounds__(kThreads, 1) skinny_kernel(const SkinnyParams 
             } else {  // CQ == 4 codes (8-bit, gs 32... not instantiated) -- kept for completeness
                 pre.xn[0] = make_uint4(0u, 0u, 0u, 0u);
             }
+            if constexpr (!SB_TMA) {
 #pragma unroll
-            for (int q = 0; q < RT; q++) {
+                for (int q = 0; q < RT; q++) {
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int lr = 16 * q + g + 8 * h;
-                    const bool ok = gv && lr < nr;
-                    const int64_t gi = (r0 + ra + lr) * (int64_t)p.G + grp;
-                    pre.sc[q][h] = ok ? (uint32_t)__ldg(p.scales + gi) : 0u;
-                    pre.bi[q][h] = ok ? (uint32_t)__ldg(p.biases + gi) : 0u;
+                    for (int h = 0; h < 2; h++) {
+                        const int lr = 16 * q + g + 8 * h;
+                        const bool ok = gv && lr < nr;
+                        const int64_t gi = (r0 + ra + lr) * (int64_t)p.G + grp;
+                        pre.sc[q][h] = ok ? (uint32_t)__ldg(p.scales + gi) : 0u;
+                        pre.bi[q][h] = ok ? (uint32_t)__ldg(p.biases + gi) : 0u;
+                    }
                 }
             }
         };
@@ -188,38 +213,47 @@ __global__ void __launch_bounds__(kThreads, 1) skinny_kernel(const SkinnyParams 
             if (nr > rb_rows) nr = rb_rows;
             const int nrt = (nr + 15) >> 4;
 
-            // ---- B fragments: permute this thread's quarter of x into LOP3 pair order; sum(x) per token
+            // ---- B fragments: permute this thread's quarter of x into LOP3 pair order.  sum(x) over the group
+            //      for tokens (2t, 2t+1) = one more MMA chain against an all-ones A fragment (exact: 1.0 * x)
             uint32_t bfrag[P];
             float xs0, xs1;
             {
                 const uint32_t* n32 = reinterpret_cast<const uint32_t*>(pre.xn);  // n32[i] = codes (2i, 2i+1)
-                float sx = 0.f;
-#pragma unroll
-                for (int i = 0; i < CQ / 2; i++) {
-                    sx += __uint_as_float(n32[i] << 16);
-                    sx += __uint_as_float(n32[i] & 0xffff0000u);
-                }
-                sx += __shfl_xor_sync(0xffffffffu, sx, 1);
-                sx += __shfl_xor_sync(0xffffffffu, sx, 2);  // every lane of token-group g: sum over the whole group
-                xs0 = __shfl_sync(0xffffffffu, sx, (2 * t) * 4);      // token 2t   (column of d0 / d2)
-                xs1 = __shfl_sync(0xffffffffu, sx, (2 * t + 1) * 4);  // token 2t+1 (column of d1 / d3)
 #pragma unroll
                 for (int q = 0; q < P; q++) {
                     const int ia = pair_a<BITS>(q), ib = pair_b<BITS>(q);
                     const uint32_t sel = ((ia & 1) ? 0x32u : 0x10u) | (((ib & 1) ? 0x76u : 0x54u) << 8);
                     bfrag[q] = __byte_perm(n32[ia >> 1], n32[ib >> 1], sel);
                 }
+                float d1[4] = {0.f, 0.f, 0.f, 0.f};
+                constexpr uint32_t kOnes = 0x3F803F80u;
+#pragma unroll
+                for (int st = 0; st < S; st++) mma16816(d1, kOnes, kOnes, kOnes, kOnes, bfrag[2 * st], bfrag[2 * st + 1]);
+                xs0 = d1[0];
+                xs1 = d1[1];
             }
 
             mbar_wait(&full_bar[s], phase);
             if (grp < p.G) {  // warp-uniform: the last k-tile may hold fewer than 16 groups
-                const uint32_t base = ring_u32 + (uint32_t)s * slot_bytes + (uint32_t)warp * (QW * 16) + (uint32_t)t * (QW * 4);
+                // this thread's quarter inside the stage: byte `off` of the row piece -> TMA box off/128, 16-byte chunk
+                // (off%128)/16 XOR (row & 7) (SWIZZLE_128B; rows 16q+g and 16q+g+8 share row&7 == g)
+                constexpr int NPC = QW == 8 ? 2 : 1;  // 16-byte pieces per quarter
+                uint32_t toff[NPC];
+#pragma unroll
+                for (int v = 0; v < NPC; v++) {
+                    const uint32_t off = (uint32_t)warp * (QW * 16) + (uint32_t)t * (QW * 4) + 16u * v;
+                    toff[v] = (off >> 7) * ((uint32_t)p.rs * 128u) + ((((off & 127u) >> 4) ^ (uint32_t)g) << 4) + (off & 15u) +
+                              (uint32_t)g * 128u;
+                }
+                const uint32_t base = ring_u32 + (uint32_t)s * slot_bytes;
+                const uint32_t sbase = ring_u32 + (uint32_t)s * slot_bytes + p.sb_off + (uint32_t)warp * 2u;
+                (void)sbase;
 #pragma unroll
                 for (int q = 0; q < RT; q++) {
                     if (q < nrt) {  // warp-uniform
                         uint32_t wl[QW], wh[QW];
-                        const uint32_t al = base + (uint32_t)(16 * q + g) * p.pitch;
-                        const uint32_t ah = al + 8u * p.pitch;
+                        const uint32_t al = base + toff[0] + (uint32_t)q * 2048u;
+                        const uint32_t ah = al + 1024u;
                         if constexpr (QW == 1) {
                             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wl[0]) : "r"(al));
                             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wh[0]) : "r"(ah));
@@ -229,7 +263,8 @@ __global__ void __launch_bounds__(kThreads, 1) skinny_kernel(const SkinnyParams 
                         } else {
 #pragma unroll
                             for (int v = 0; v < QW / 4; v++) {
-                                const uint4 a = lds128(al + 16 * v), b = lds128(ah + 16 * v);
+                                const uint32_t dv = toff[v < NPC ? v : 0] - toff[0];
+                                const uint4 a = lds128(al + dv), b = lds128(ah + dv);
                                 wl[4 * v] = a.x; wl[4 * v + 1] = a.y; wl[4 * v + 2] = a.z; wl[4 * v + 3] = a.w;
                                 wh[4 * v] = b.x; wh[4 * v + 1] = b.y; wh[4 * v + 2] = b.z; wh[4 * v + 3] = b.w;
                             }
@@ -262,9 +297,20 @@ __global__ void __launch_bounds__(kThreads, 1) skinny_kernel(const SkinnyParams 
                             if constexpr (BITS == 8)
                                 mma16816(d, al2b[0], ah2b[0], al2b[1], ah2b[1], bfrag[2 * st], bfrag[2 * st + 1]);
                         }
-                        const float sl = __uint_as_float(pre.sc[q][0] << 16), sh_ = __uint_as_float(pre.sc[q][1] << 16);
-                        const float cl = fmaf(-OFF, sl, __uint_as_float(pre.bi[q][0] << 16));
-                        const float ch = fmaf(-OFF, sh_, __uint_as_float(pre.bi[q][1] << 16));
+                        uint32_t s0, s1, b0, b1;
+                        if constexpr (SB_TMA) {
+                            // [rs][16] bf16 boxes: (row, this warp's group); rows beyond the tensor are zero-filled
+                            const uint32_t sa = sbase + (uint32_t)(16 * q + g) * 32u;
+                            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(s0) : "r"(sa));
+                            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(s1) : "r"(sa + 256u));
+                            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(b0) : "r"(sa + (uint32_t)p.rs * 32u));
+                            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(b1) : "r"(sa + (uint32_t)p.rs * 32u + 256u));
+                        } else {
+                            s0 = pre.sc[q][0]; s1 = pre.sc[q][1]; b0 = pre.bi[q][0]; b1 = pre.bi[q][1];
+                        }
+                        const float sl = __uint_as_float(s0 << 16), sh_ = __uint_as_float(s1 << 16);
+                        const float cl = fmaf(-OFF, sl, __uint_as_float(b0 << 16));
+                        const float ch = fmaf(-OFF, sh_, __uint_as_float(b1 << 16));
                         yacc[q][0] = fmaf(sl, d[0], fmaf(cl, xs0, yacc[q][0]));
                         yacc[q][1] = fmaf(sl, d[1], fmaf(cl, xs1, yacc[q][1]));
                         yacc[q][2] = fmaf(sh_, d[2], fmaf(ch, xs0, yacc[q][2]));
@@ -317,9 +363,10 @@ __global__ void __launch_bounds__(kThreads, 1) skinny_kernel(const SkinnyParams 
 }
 
 struct Plan {
-    bool ok;
+    bool ok, sb_tma;
     int qw, rs, n_kt;
-    uint32_t piece, pitch;
+    uint32_t piece, sb_off, slot;
+    int nbox;
     size_t smem;
 };
 
@@ -336,29 +383,41 @@ Plan make_plan(int64_t N, int64_t K, int bits, int gs) {
     pl.piece = (uint32_t)(kWarps * gs * bits / 8);
     if (pl.piece % 16) return pl;
     pl.n_kt = (int)((G + kWarps - 1) / kWarps);
-    const uint32_t pad = pl.qw == 8 ? 16u : (uint32_t)pl.qw * 16u;
-    pl.pitch = pl.piece + pad;
-    int rs = (int)((36 * 1024) / pl.pitch) & ~15;
+    if (pl.piece % 128) return pl;
+    pl.nbox = (int)(pl.piece / 128);
+    int rs = (int)((32 * 1024) / pl.piece) & ~15;
     if (rs > kMaxRS) rs = kMaxRS;
     if (rs < 16) return pl;
     pl.rs = rs;
-    pl.smem = (size_t)kStages * rs * pl.pitch + 2 * kStages * 8 + (size_t)kWarps * rs * 8 * 4 + 16;
+    pl.sb_tma = (G * 2) % 16 == 0;  // TMA needs a 16-byte row pitch for the scale / bias matrices
+    pl.sb_off = (uint32_t)rs * pl.piece;
+    pl.slot = pl.sb_off + 2u * (uint32_t)rs * 32u;  // multiple of 1024: every slot keeps the swizzle alignment
+    pl.smem = (size_t)kStages * pl.slot + 2 * kStages * 8 + (size_t)kWarps * rs * 8 * 4 + 16 + 1024;
     if (pl.smem > 227 * 1024) return pl;
     (void)N;
     pl.ok = true;
     return pl;
 }
 
-template <int BITS, int QW> int launch_inst(const SkinnyParams& p, size_t smem, int grid, cudaStream_t st) {
+template <int BITS, int QW, bool SB_TMA>
+int launch_inst2(const CUtensorMap& tw, const CUtensorMap& ts, const CUtensorMap& tb, const SkinnyParams& p, size_t smem, int grid,
+                 cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(skinny_kernel<BITS, QW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(skinny_kernel<BITS, QW, SB_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return check_cuda(e);
         configured = true;
     }
-    skinny_kernel<BITS, QW><<<grid, kThreads, smem, st>>>(p);
+    skinny_kernel<BITS, QW, SB_TMA><<<grid, kThreads, smem, st>>>(tw, ts, tb, p);
     count_launch();
     return check_cuda(cudaGetLastError());
+}
+
+template <int BITS, int QW>
+int launch_inst(bool sb_tma, const CUtensorMap& tw, const CUtensorMap& ts, const CUtensorMap& tb, const SkinnyParams& p,
+                size_t smem, int grid, cudaStream_t st) {
+    return sb_tma ? launch_inst2<BITS, QW, true>(tw, ts, tb, p, smem, grid, st)
+                  : launch_inst2<BITS, QW, false>(tw, ts, tb, p, smem, grid, st);
 }
 
 }  // namespace
@@ -369,7 +428,7 @@ bool skinny_supported(int64_t M, int64_t N, int64_t K, int bits, int gs, int dty
     if (((uintptr_t)x | (uintptr_t)w) & 15) return false;
     if ((uintptr_t)y & 1) return false;
     if ((K * 2) % 16) return false;
-    return make_plan(N, K, bits, gs).ok;
+    return make_plan(N, K, bits, gs).ok && tma_encode_available();
 }
 
 int launch_skinny(const void* x, const uint32_t* w, const void* s, const void* b, const void* bias, void* y, int64_t M,
@@ -387,8 +446,24 @@ int launch_skinny(const void* x, const uint32_t* w, const void* s, const void* b
     p.n_kt = pl.n_kt;
     p.rs = pl.rs;
     p.row_bytes = (uint32_t)(K * bits / 8);
-    p.piece_bytes = pl.piece;
-    p.pitch = pl.pitch;
+    p.piece_words = pl.piece / 4;
+    p.nbox = pl.nbox;
+    p.sb_off = pl.sb_off;
+    p.slot_bytes = pl.slot;
+    CUtensorMap tw, ts, tb;
+    memset(&ts, 0, sizeof(ts));
+    memset(&tb, 0, sizeof(tb));
+    {
+        const uint64_t words = (uint64_t)(K * bits / 32);
+        if (!encode_tensor_map_2d(&tw, /*uint32*/ 1, w, words, (uint64_t)N, words * 4, 32, (uint32_t)pl.rs, true))
+            return GBXQ_EUNSUPPORTED;
+    }
+    bool sb_tma = pl.sb_tma && !(((uintptr_t)s | (uintptr_t)b) & 15);
+    if (sb_tma) {
+        const uint64_t G = (uint64_t)(K / gs);
+        sb_tma = encode_tensor_map_2d(&ts, /*bf16*/ 0, s, G, (uint64_t)N, G * 2, kWarps, (uint32_t)pl.rs, false) &&
+                 encode_tensor_map_2d(&tb, 0, b, G, (uint64_t)N, G * 2, kWarps, (uint32_t)pl.rs, false);
+    }
     int grid = device_sm_count();
     if (grid > N) grid = (int)N;
     for (int64_t m0 = 0; m0 < M; m0 += 8) {
@@ -397,14 +472,14 @@ int launch_skinny(const void* x, const uint32_t* w, const void* s, const void* b
         p.M = (int)((M - m0) < 8 ? (M - m0) : 8);
         int rc = GBXQ_EUNSUPPORTED;
         switch (bits * 16 + pl.qw) {
-            case 4 * 16 + 1: rc = launch_inst<4, 1>(p, pl.smem, grid, st); break;
-            case 4 * 16 + 2: rc = launch_inst<4, 2>(p, pl.smem, grid, st); break;
-            case 4 * 16 + 4: rc = launch_inst<4, 4>(p, pl.smem, grid, st); break;
-            case 2 * 16 + 1: rc = launch_inst<2, 1>(p, pl.smem, grid, st); break;
-            case 2 * 16 + 2: rc = launch_inst<2, 2>(p, pl.smem, grid, st); break;
-            case 8 * 16 + 2: rc = launch_inst<8, 2>(p, pl.smem, grid, st); break;
-            case 8 * 16 + 4: rc = launch_inst<8, 4>(p, pl.smem, grid, st); break;
-            case 8 * 16 + 8: rc = launch_inst<8, 8>(p, pl.smem, grid, st); break;
+            case 4 * 16 + 1: rc = launch_inst<4, 1>(sb_tma, tw, ts, tb, p, pl.smem, grid, st); break;
+            case 4 * 16 + 2: rc = launch_inst<4, 2>(sb_tma, tw, ts, tb, p, pl.smem, grid, st); break;
+            case 4 * 16 + 4: rc = launch_inst<4, 4>(sb_tma, tw, ts, tb, p, pl.smem, grid, st); break;
+            case 2 * 16 + 1: rc = launch_inst<2, 1>(sb_tma, tw, ts, tb, p, pl.smem, grid, st); break;
+            case 2 * 16 + 2: rc = launch_inst<2, 2>(sb_tma, tw, ts, tb, p, pl.smem, grid, st); break;
+            case 8 * 16 + 2: rc = launch_inst<8, 2>(sb_tma, tw, ts, tb, p, pl.smem, grid, st); break;
+            case 8 * 16 + 4: rc = launch_inst<8, 4>(sb_tma, tw, ts, tb, p, pl.smem, grid, st); break;
+            case 8 * 16 + 8: rc = launch_inst<8, 8>(sb_tma, tw, ts, tb, p, pl.smem, grid, st); break;
         }
         if (rc != GBXQ_OK) return rc;
     }
