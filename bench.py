@@ -139,6 +139,7 @@ def run_gbxq(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    ops.set_pdl_mode(args.pdl)
     dims, plan = build_plan(args)
     full_plan = plan
     plan = shard_plan(plan, world) if world > 1 else plan
@@ -384,6 +385,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pdl", type=int, default=2, help="GBXQ_OPT_PDL (0 plain launches, 1 PDL, 2 PDL + early weight streaming)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -9,7 +9,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgbxq.so")
 
 BF16, F16, F32 = 0, 1, 2
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_GEMV, KERNEL_GEMM, KERNEL_SKINNY = 0, 1, 2, 3, 4
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_GEMV, KERNEL_GEMM, KERNEL_SKINNY, KERNEL_MMV, KERNEL_MMV8 = 0, 1, 2, 3, 4, 5, 6
+OPT_PDL = 1
 AR_MAX_CTAS = 32
 
 EXPORTS = (
@@ -23,6 +24,8 @@ EXPORTS = (
     "gbxq_dequantize",
     "gbxq_select_kernel",
     "gbxq_launch_count",
+    "gbxq_set_option",
+    "gbxq_get_option",
     "gbxq_allreduce_oneshot",
 )
 
@@ -71,6 +74,10 @@ def get() -> ctypes.CDLL:
     lib.gbxq_select_kernel.restype = ci
     lib.gbxq_select_kernel.argtypes = [i64, i64, i64, ci, ci, ci]
     lib.gbxq_launch_count.restype = ctypes.c_uint64
+    lib.gbxq_set_option.restype = ci
+    lib.gbxq_set_option.argtypes = [ci, ci]
+    lib.gbxq_get_option.restype = ci
+    lib.gbxq_get_option.argtypes = [ci]
     lib.gbxq_allreduce_oneshot.restype = ci
     lib.gbxq_allreduce_oneshot.argtypes = [vp, vp, i64, ci, vp, vp, i64, ci, ci, u32, vp]
     if lib.gbxq_abi_version() != 1:

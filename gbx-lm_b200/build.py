@@ -22,6 +22,8 @@ SOURCES = [
     "gbxq_generic.cu",
     "gbxq_gemv.cu",
     "gbxq_skinny.cu",
+    "gbxq_mmv.cu",
+    "gbxq_mmv8.cu",
     "gbxq_gemm_sm100.cu",
     "gbxq_allreduce.cu",
 ]

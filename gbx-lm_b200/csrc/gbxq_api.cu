@@ -34,6 +34,9 @@ static int select(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype, 
     const bool skinny_ok = skinny_supported(M, N, K, bits, gs, dtype, x, w, y);
     const bool gemv_ok = gemv_supported(M, N, K, bits, gs, dtype, x, w, y);
     const bool gemm_ok = gemm_supported(M, N, K, bits, gs, dtype, x, w, y);
+    // tensor-pipe matrix-vector kernels: 1..4 tokens; the integer one is the faster (profiles/)
+    if (M <= 4 && mmv8_supported(M, N, K, bits, gs, dtype, x, w, y)) return GBXQ_KERNEL_MMV8;
+    if (M <= 4 && mmv_supported(M, N, K, bits, gs, dtype, x, w, y)) return GBXQ_KERNEL_MMV;
     // measured on B200 (profiles/): the FMA-pipe GEMV wins at M <= 2, the tensor-pipe skinny kernel costs the
     // same for 1..8 tokens and wins from M = 3
     if (gemv_ok && M <= 2) return GBXQ_KERNEL_GEMV;
@@ -72,6 +75,23 @@ int gbxq_last_cuda_error(void) { return (int)g_last_cuda_error; }
 const char* gbxq_last_cuda_error_string(void) { return cudaGetErrorString(g_last_cuda_error); }
 uint64_t gbxq_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+// Development aid (not in gbxq.h): the next `launches` mmv8 launches write 8 %globaltimer stamps each (CTA 0, thread 0)
+// to `buf_dev`: entry, after griddepcontrol.wait, after the prologue, first stage landed, main loop done, CTA barrier,
+// exit.  tools/timeline.py prints them.
+void gbxq_debug_timeline(unsigned long long* buf_dev, int launches) { mmv8_debug_timeline(buf_dev, launches); }
+
+int gbxq_set_option(int key, int value) {
+    if (key == GBXQ_OPT_PDL) {
+        mmv_set_pdl_mode(value);
+        return GBXQ_OK;
+    }
+    return GBXQ_EUNSUPPORTED;
+}
+int gbxq_get_option(int key) {
+    if (key == GBXQ_OPT_PDL) return mmv_get_pdl_mode();
+    return GBXQ_EUNSUPPORTED;
+}
+
 size_t gbxq_workspace_bytes(int64_t, int64_t, int64_t, int, int, int) { return 0; }
 
 int gbxq_select_kernel(int64_t M, int64_t N, int64_t K, int bits, int group_size, int dtype) {
@@ -106,6 +126,12 @@ int gbxq_qmm_ex(const void* x, const uint32_t* qweight, const void* scales, cons
         case GBXQ_KERNEL_SKINNY:
             if (!skinny_supported(M, N, K, bits, group_size, dtype, x, qweight, y)) return GBXQ_EUNSUPPORTED;
             return launch_skinny(x, qweight, scales, biases, bias, y, M, N, K, bits, group_size, st);
+        case GBXQ_KERNEL_MMV8:
+            if (!mmv8_supported(M, N, K, bits, group_size, dtype, x, qweight, y)) return GBXQ_EUNSUPPORTED;
+            return launch_mmv8(x, qweight, scales, biases, bias, y, M, N, K, bits, group_size, st);
+        case GBXQ_KERNEL_MMV:
+            if (!mmv_supported(M, N, K, bits, group_size, dtype, x, qweight, y)) return GBXQ_EUNSUPPORTED;
+            return launch_mmv(x, qweight, scales, biases, bias, y, M, N, K, bits, group_size, st);
         case GBXQ_KERNEL_GEMM:
             if (!gemm_supported(M, N, K, bits, group_size, dtype, x, qweight, y)) return GBXQ_EUNSUPPORTED;
             return launch_gemm(x, qweight, scales, biases, bias, y, M, N, K, bits, group_size, st);

@@ -159,6 +159,17 @@ bool skinny_supported(int64_t M, int64_t N, int64_t K, int bits, int gs, int dty
                       const void* y);
 int launch_skinny(const void* x, const uint32_t* w, const void* s, const void* b, const void* bias, void* y, int64_t M,
                   int64_t N, int64_t K, int bits, int gs, cudaStream_t st);
+bool mmv_supported(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype, const void* x, const void* w,
+                   const void* y);
+int launch_mmv(const void* x, const uint32_t* w, const void* s, const void* b, const void* bias, void* y, int64_t M,
+               int64_t N, int64_t K, int bits, int gs, cudaStream_t st);
+bool mmv8_supported(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype, const void* x, const void* w,
+                    const void* y);
+int launch_mmv8(const void* x, const uint32_t* w, const void* s, const void* b, const void* bias, void* y, int64_t M,
+                int64_t N, int64_t K, int bits, int gs, cudaStream_t st);
+void mmv8_debug_timeline(unsigned long long* buf, int launches);
+void mmv_set_pdl_mode(int mode);
+int mmv_get_pdl_mode();
 bool gemm_supported(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype, const void* x, const void* w,
                     const void* y);
 int launch_gemm(const void* x, const uint32_t* w, const void* s, const void* b, const void* bias, void* y, int64_t M,

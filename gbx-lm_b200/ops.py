@@ -18,7 +18,7 @@ import torch
 from . import _lib
 
 _DT = {torch.bfloat16: _lib.BF16, torch.float16: _lib.F16, torch.float32: _lib.F32}
-_KERNELS = {"auto": 0, "generic": 1, "gemv": 2, "gemm": 3, "skinny": 4}
+_KERNELS = {"auto": 0, "generic": 1, "gemv": 2, "gemm": 3, "skinny": 4, "mmv": 5, "mmv8": 6}
 
 
 def _dt(t: torch.Tensor) -> int:
@@ -178,7 +178,13 @@ def dequantize(w: torch.Tensor, scales: torch.Tensor, biases: torch.Tensor, grou
 def select_kernel(m: int, n: int, k: int, bits: int, group_size: int, dtype: torch.dtype = torch.bfloat16) -> str:
     rc = _lib.get().gbxq_select_kernel(m, n, k, bits, group_size, _DT[dtype])
     _lib.check(min(rc, 0), "gbxq_select_kernel")
-    return {1: "generic", 2: "gemv", 3: "gemm", 4: "skinny"}[rc]
+    return {1: "generic", 2: "gemv", 3: "gemm", 4: "skinny", 5: "mmv", 6: "mmv8"}[rc]
+
+
+def set_pdl_mode(mode: int) -> None:
+    """GBXQ_OPT_PDL (include/gbxq.h): 0 plain launches, 1 PDL with conservative waits, 2 (default) PDL with the
+    frozen weights streamed ahead of the wait."""
+    _lib.check(_lib.get().gbxq_set_option(_lib.OPT_PDL, int(mode)), "gbxq_set_option")
 
 
 def launch_count() -> int:

@@ -19,7 +19,8 @@
  *     Inputs are never written.  Outputs are fully overwritten.
  *   - Calls only ENQUEUE work on `stream` (a cudaStream_t passed as void*; NULL = legacy default
  *     stream) and return; they never synchronise, never allocate device memory and keep no
- *     global mutable state, so they are CUDA-graph capturable and thread-safe across streams.
+ *     global mutable state besides the options of gbxq_set_option, so they are CUDA-graph capturable
+ *     and thread-safe across streams.
  *   - Return value: GBXQ_OK (0) or a negative gbxq_status.  Nothing throws.
  *   - Tensor layout = MLX affine quantisation as emitted by gba2mlx (gbx_lm/gba2mlx.py:47-65,
  *     gbx_lm/utils.py:828-843):
@@ -68,8 +69,23 @@ typedef enum gbxq_kernel {
     GBXQ_KERNEL_GENERIC = 1, /* shape-agnostic warp-per-row kernel (all dtypes)            */
     GBXQ_KERNEL_GEMV = 2,    /* TMA-bulk ring streaming GEMV on the FMA pipe, M tiles of 1/2 */
     GBXQ_KERNEL_GEMM = 3,    /* tcgen05/TMEM tensor-core GEMM with in-kernel dequant (bf16) */
-    GBXQ_KERNEL_SKINNY = 4   /* mma.sync skinny matmul, 8 tokens per pass, 2/4/8-bit (bf16)  */
+    GBXQ_KERNEL_SKINNY = 4,  /* mma.sync skinny matmul, 8 tokens per pass, 2/4/8-bit (bf16)  */
+    GBXQ_KERNEL_MMV = 5,     /* bf16 tensor-pipe decode matrix-vector kernel, 1..4 tokens, 2/4/8-bit, PDL */
+    GBXQ_KERNEL_MMV8 = 6     /* integer tensor-pipe (IMMA u8 x s8) decode kernel: codes used in place, activations as
+                                per-group 15-bit block fixed point; 1..4 tokens, 2/4/8-bit (bf16 in/out), PDL */
 } gbxq_kernel;
+
+/* Process-wide options (gbxq_set_option / gbxq_get_option). */
+typedef enum gbxq_option {
+    /* Programmatic dependent launch of the decode kernels:
+     *   0  plain stream-ordered launches
+     *   1  PDL launch attribute; every global read waits for the preceding kernels of the stream
+     *   2  (default) as 1, but qweight/scales/biases are streamed BEFORE that wait: the caller guarantees
+     *      that no kernel still in flight on the stream writes them (true for QuantizedLinear: its
+     *      parameters are frozen, quantized_linear_gba.py:57-58,162-166).  x, bias and y are always
+     *      touched after the wait. */
+    GBXQ_OPT_PDL = 1
+} gbxq_option;
 
 /* Library / ABI identification. */
 int gbxq_abi_version(void);
@@ -107,6 +123,10 @@ int gbxq_dequantize(const uint32_t* qweight, const void* scales, const void* bia
 
 /* Which kernel family GBXQ_KERNEL_AUTO picks for these arguments (a gbxq_kernel value, or <0). */
 int gbxq_select_kernel(int64_t M, int64_t N, int64_t K, int bits, int group_size, int dtype);
+
+/* Set / read a gbxq_option.  Returns GBXQ_OK / the value, or GBXQ_EUNSUPPORTED for an unknown key. */
+int gbxq_set_option(int key, int value);
+int gbxq_get_option(int key);
 
 /* Number of kernel launches libgbxq has enqueued from this process (monotonic; for benches). */
 uint64_t gbxq_launch_count(void);

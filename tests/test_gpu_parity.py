@@ -104,6 +104,118 @@ def test_qmm_vs_oracle_small(cuda_device, kernel, bits, gs):
         _run_case(g, cuda_device, kernel, bits, gs, M, 70, 1024, seed=bits * 31 + gs + M)
 
 
+def _mmv_ok(bits, gs, K=1024, kernel="mmv"):
+    if kernel == "mmv8":
+        return bits in (2, 4, 8) and not (bits == 2 and gs == 32) and (K // gs) % 8 == 0
+    return bits in (2, 4, 8) and gs * bits // 32 in (4, 8, 16) and (K // gs) % 8 == 0
+
+
+MMV_KERNELS = ("mmv", "mmv8")
+
+
+@pytest.mark.parametrize("kernel", MMV_KERNELS)
+@pytest.mark.parametrize("bits", (2, 4, 8))
+@pytest.mark.parametrize("gs", GS)
+def test_qmm_mmv_vs_oracle_small(cuda_device, kernel, bits, gs):
+    """Tensor-pipe decode kernels ("slice" MMA layout; bf16 HMMA and integer IMMA) at M = 1..4, every supported packing."""
+    g = _ops()
+    if not _mmv_ok(bits, gs, kernel=kernel):
+        with pytest.raises(RuntimeError):  # forced kernel that cannot serve the arguments: error, not fallback
+            _run_case(g, cuda_device, kernel, bits, gs, 1, 70, 1024, seed=1)
+        return
+    for M in (1, 2, 3, 4):
+        _run_case(g, cuda_device, kernel, bits, gs, M, 70, 1024, seed=bits * 31 + gs + M, with_bias=(M == 3))
+
+
+def test_qmm_mmv8_block_fixed_point_ranges(cuda_device):
+    """The integer kernel represents x per (token, group) as 15-bit block fixed point: check wide dynamic range inside a
+    group (outlier channels), tiny and huge magnitudes, exact zeros, and that inf / nan poison only what they should."""
+    g = _ops()
+    N, K, bits, gs = 64, 1024, 4, 64
+    L = A.synth_layer(N, K, bits, gs, seed=3)
+    d = layer_to_cuda(L, cuda_device)
+    rng = np.random.default_rng(5)
+    for case in ("outliers", "tiny", "huge", "zeros", "mixed"):
+        x = rng.standard_normal((1, K)).astype(np.float32)
+        if case == "outliers":
+            x[0, ::64] *= 300.0
+        elif case == "tiny":
+            x *= 1e-30
+        elif case == "huge":
+            x *= 1e30
+        elif case == "zeros":
+            x[0, 128:512] = 0.0
+        else:
+            x *= np.exp(rng.uniform(-8, 8, size=(1, K))).astype(np.float32)
+        xb = A.f32_to_bf16_bits(x)
+        y = g.quantized_matmul(bf16_from_bits(xb, cuda_device), d["qweight"], d["scales"], d["zeros"], True, gs, bits, kernel="mmv8")
+        ref = A.quantized_matmul(xb, L["qweight"], L["scales"], L["zeros"], gs, bits, "bf16", "f64")
+        assert_close_to_truth(y, ref, f"mmv8 {case}")
+    x = rng.standard_normal((1, K)).astype(np.float32)
+    x[0, 5] = np.inf
+    y = g.quantized_matmul(bf16_from_bits(A.f32_to_bf16_bits(x), cuda_device), d["qweight"], d["scales"], d["zeros"], True, gs, bits, kernel="mmv8")
+    assert not torch.isfinite(y).any()  # every output row multiplies x[5] by a non-zero weight
+
+
+@pytest.mark.parametrize("kernel", MMV_KERNELS)
+@pytest.mark.parametrize("bits", (2, 4, 8))
+@pytest.mark.parametrize("pdl", (0, 1, 2))
+def test_qmm_mmv_model_shapes(cuda_device, kernel, bits, pdl):
+    """Config shapes: long rows (14336: 2 rows per stage), TP shards (3584), N smaller than / not a multiple
+    of the grid, single rows, the three launch modes (plain, PDL, PDL with early weight streaming)."""
+    g = _ops()
+    from gbx_lm_b200 import ops
+
+    ops.set_pdl_mode(pdl)
+    try:
+        for (N, K) in ((300, 4096), (96, 14336), (150, 3584), (1, 2048), (147, 8192), (149, 3072), (5000, 512), (1031, 1024)):
+            for M in (1, 2, 4):
+                # rows too long for W = 2*MP of them in one ring stage are served by another kernel (auto dispatch)
+                try:
+                    _run_case(g, cuda_device, kernel, bits, 64, M, N, K, seed=N + K + bits + M, with_bias=(M == 2))
+                except RuntimeError as e:
+                    assert "does not support" in str(e)  # stage too large for this kernel: auto dispatch serves it
+                    _run_case(g, cuda_device, "auto", bits, 64, M, N, K, seed=N + K + bits + M, with_bias=(M == 2))
+    finally:
+        ops.set_pdl_mode(2)
+
+
+def test_qmm_mmv_back_to_back_dependency(cuda_device):
+    """PDL: a chain y1 = W1 x, y2 = W2 y1, ... launched back to back must see its predecessor's output
+    (griddepcontrol.wait before x is read), eagerly and from a CUDA graph; bitwise equal to plain launches."""
+    g = _ops()
+    from gbx_lm_b200 import ops
+
+    K = 1024
+    Ls = [layer_to_cuda(A.synth_layer(K, K, 4, 64, seed=50 + i), cuda_device) for i in range(6)]
+    x = bf16_from_bits(A.synth_x(1, K, seed=60), cuda_device)
+
+    def chain(x):
+        h = x
+        for d in Ls:
+            h = g.quantized_matmul(h * 8, d["qweight"], d["scales"], d["zeros"], True, 64, 4, kernel="mmv")
+            h = g.quantized_matmul(h * 8, d["qweight"], d["scales"], d["zeros"], True, 64, 4, kernel="mmv8")
+        return h
+
+    ops.set_pdl_mode(0)
+    ref = chain(x)
+    ops.set_pdl_mode(2)
+    for _ in range(5):
+        assert torch.equal(chain(x), ref)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        chain(x)
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = chain(x)
+    for _ in range(5):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+
+
 @pytest.mark.parametrize("bits", (2, 4, 8))
 def test_qmm_skinny_model_shapes(cuda_device, bits):
     """mma.sync skinny kernel on the config shapes: ragged k-tiles (3584/64 = 56 groups = 3.5 tiles),
@@ -189,8 +301,10 @@ def test_qmm_golden_fixtures(cuda_device, case):
     z = bf16_from_bits(np.array(case["zeros_bf16"], dtype=np.uint16), cuda_device)
     x = bf16_from_bits(np.array(case["x_bf16"], dtype=np.uint16), cuda_device)
     gold = A.bf16_bits_to_f32(np.array(case["y_bf16"], dtype=np.uint16))
-    for kernel in ("generic", "gemv", "skinny"):
+    for kernel in ("generic", "gemv", "skinny", "mmv", "mmv8"):
         if kernel == "skinny" and not _skinny_ok(case["bits"], case["group_size"]):
+            continue
+        if kernel in MMV_KERNELS and not (_mmv_ok(case["bits"], case["group_size"], x.shape[-1], kernel) and x.shape[0] <= 4):
             continue
         y = g.quantized_matmul(x, w, s, z, True, case["group_size"], case["bits"], kernel=kernel).float().cpu().numpy()
         ulp = np.maximum(np.abs(gold) * 2.0 ** -7, np.abs(gold).max() * 2.0 ** -9)
@@ -288,6 +402,15 @@ def test_full_size_8b_gate_proj_properties(cuda_device):
     assert (ys.float() - y.float()).abs().max() <= 2.0 ** -7 * y.float().abs().max()
     assert torch.equal(ys, g.quantized_matmul(x, qw, s, z, True, gs, bits, kernel="skinny"))
     assert torch.equal(ys[:1], g.quantized_matmul(x[:1], qw, s, z, True, gs, bits, kernel="skinny"))
+    # so does the tensor-pipe decode kernel (auto dispatch at M <= 4), sampled rows against the oracle again
+    for kern in MMV_KERNELS:
+        ym = g.quantized_matmul(x, qw, s, z, True, gs, bits, kernel=kern)
+        assert_close_to_truth(ym[:, torch.from_numpy(rows).to(cuda_device)], ref, kern + " sampled rows")
+        assert (ym.float() - y.float()).abs().max() <= 2.0 ** -7 * y.float().abs().max()
+        assert torch.equal(ym, g.quantized_matmul(x, qw, s, z, True, gs, bits, kernel=kern))  # run-to-run reproducible
+        ym1 = g.quantized_matmul(x[:1], qw, s, z, True, gs, bits, kernel=kern)
+        assert (ym1.float() - ym[:1].float()).abs().max() <= 2.0 ** -7 * y.float().abs().max()
+    assert torch.equal(ym, g.quantized_matmul(x, qw, s, z, True, gs, bits))  # auto dispatch at M <= 4 = the integer kernel
 
 
 def test_cuda_graph_capture(cuda_device):

@@ -32,7 +32,7 @@ def bench_shape(n, k, bits, gs, m, kernel, dev, iters=30, min_bytes=320 << 20):
         ss.append(s)
         zs.append((-s.float() * (nb / 2.0)).to(torch.bfloat16))
     x = torch.randn((m, k), generator=gen, device=dev).to(torch.bfloat16)
-    kid = {"auto": 0, "generic": 1, "gemv": 2, "gemm": 3, "skinny": 4}[kernel]
+    kid = {"auto": 0, "generic": 1, "gemv": 2, "gemm": 3, "skinny": 4, "mmv": 5, "mmv8": 6}[kernel]
 
     def run(i):
         j = i % copies
@@ -70,6 +70,8 @@ def main():
     shapes8b = [("q/o", 4096, 4096), ("k/v", 1024, 4096), ("gate/up", 14336, 4096), ("down", 4096, 14336)]
     shapes70b = [("q/o", 8192, 8192), ("k/v", 1024, 8192), ("gate/up", 28672, 8192), ("down", 8192, 28672)]
     shapes = shapes70b if args.shapes == "70b" else shapes8b
+    if args.shapes == "big":  # asymptotic streaming rate: ~8x gate_proj rows
+        shapes = [("big", 114688, 4096), ("bigk", 32768, 14336)]
     combos = [(4, 64), (2, 64)] if args.quick else [(4, 64), (4, 128), (2, 64), (2, 128), (3, 64), (6, 64), (8, 64), (4, 32), (2, 32)]
     ms = [int(v) for v in args.ms.split(",")]
     rows = []
