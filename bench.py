@@ -170,12 +170,27 @@ def run_gbxq(args):
 
     outs = [None]
 
+    # the callers' launch structure (gbx_lm/models/qllama.py:76,115): q|k|v and gate|up read the same activations
+    # and go out as ONE grouped call each, o_proj and down_proj as single calls -> 4 library calls per block
+    calls, i = [], 0
+    while i < len(layers):
+        names = [p for p, _ in layers[i:i + 3]]
+        if args.grouped and names == ["q_proj", "k_proj", "v_proj"]:
+            calls.append(("qkv", [m for _, m in layers[i:i + 3]])); i += 3
+        elif args.grouped and names[:2] == ["gate_proj", "up_proj"]:
+            calls.append(("gate_up", [m for _, m in layers[i:i + 2]])); i += 2
+        else:
+            calls.append((layers[i][0], [layers[i][1]])); i += 1
+
     def step():
         y = None
-        for p, m in layers:
-            y = m(xbuf[m.input_dims])
-            if world > 1 and p in ("o_proj", "down_proj"):
-                dist.all_reduce(y)
+        for p, ms in calls:
+            if len(ms) == 1:
+                y = ms[0](xbuf[ms[0].input_dims])
+                if world > 1 and p in ("o_proj", "down_proj"):
+                    dist.all_reduce(y)
+            else:
+                y = ops.quantized_matmul_grouped(xbuf[ms[0].input_dims], ms)[0]
         outs[0] = y
 
     # ---- warm-up eagerly (also sets kernel attributes), then capture one step into a CUDA graph
@@ -274,6 +289,7 @@ def run_gbxq(args):
                         f"forwards/step (stored bpw {W.stored_bpw(full_plan):.3f})",
             "bytes_per_step": bytes_step, "l2": "inputs larger than L2 (weights per step >> 126 MB)",
             "parallelism": f"tp{world}" if world > 1 else "single", "launch": "cuda_graph",
+            "calls_per_step": len(calls), "grouped_qkv_gate_up": bool(args.grouped),
         },
         "decode_tok_s_qmm_only": round(1e3 / ms_step * M, 2),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
@@ -385,6 +401,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--grouped", type=int, default=1, help="1: q|k|v and gate|up as one gbxq_qmm_grouped call each (as the model does)")
     ap.add_argument("--pdl", type=int, default=2, help="GBXQ_OPT_PDL (0 plain launches, 1 PDL, 2 PDL + early weight streaming)")
     args = ap.parse_args()
     if args.impl == "reference":

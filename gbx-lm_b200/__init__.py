@@ -8,5 +8,5 @@ there is no CPU, Triton or PyTorch fallback."""
 
 __version__ = "0.1.0"
 
-from .ops import dequantize, quantized_matmul  # noqa: F401
+from .ops import dequantize, quantized_matmul, quantized_matmul_grouped  # noqa: F401
 from .quantized_linear import QuantizedLinear  # noqa: F401

@@ -20,6 +20,7 @@ EXPORTS = (
     "gbxq_last_cuda_error_string",
     "gbxq_qmm",
     "gbxq_qmm_ex",
+    "gbxq_qmm_grouped",
     "gbxq_workspace_bytes",
     "gbxq_dequantize",
     "gbxq_select_kernel",
@@ -28,6 +29,18 @@ EXPORTS = (
     "gbxq_get_option",
     "gbxq_allreduce_oneshot",
 )
+
+
+MAX_SEGMENTS = 4
+
+
+class Segment(ctypes.Structure):
+    """struct gbxq_segment (include/gbxq.h)."""
+
+    _fields_ = [
+        ("qweight", ctypes.c_void_p), ("scales", ctypes.c_void_p), ("biases", ctypes.c_void_p), ("bias", ctypes.c_void_p),
+        ("y", ctypes.c_void_p), ("N", ctypes.c_int64), ("bits", ctypes.c_int), ("group_size", ctypes.c_int),
+    ]
 
 
 class GbxqError(RuntimeError):
@@ -67,6 +80,8 @@ def get() -> ctypes.CDLL:
     lib.gbxq_qmm.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, ci, ci, ci, vp, sz, vp]
     lib.gbxq_qmm_ex.restype = ci
     lib.gbxq_qmm_ex.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, ci, ci, ci, ci, vp, sz, vp]
+    lib.gbxq_qmm_grouped.restype = ci
+    lib.gbxq_qmm_grouped.argtypes = [ctypes.POINTER(Segment), ci, vp, i64, i64, ci, vp]
     lib.gbxq_workspace_bytes.restype = sz
     lib.gbxq_workspace_bytes.argtypes = [i64, i64, i64, ci, ci, ci]
     lib.gbxq_dequantize.restype = ci

@@ -24,6 +24,7 @@ SOURCES = [
     "gbxq_skinny.cu",
     "gbxq_mmv.cu",
     "gbxq_mmv8.cu",
+    "gbxq_mmv8_grouped.cu",
     "gbxq_gemm_sm100.cu",
     "gbxq_allreduce.cu",
 ]

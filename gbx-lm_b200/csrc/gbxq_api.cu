@@ -146,6 +146,35 @@ int gbxq_qmm(const void* x, const uint32_t* qweight, const void* scales, const v
                        workspace, workspace_bytes, stream);
 }
 
+int gbxq_qmm_grouped(const gbxq_segment* segs, int nseg, const void* x, int64_t M, int64_t K, int dtype, void* stream) {
+    if (nseg < 0) return GBXQ_ESHAPE;
+    if (nseg == 0) return GBXQ_OK;
+    if (!segs) return GBXQ_ENULL;
+    const size_t esz = dtype == GBXQ_F32 ? 4 : 2;
+    for (int i = 0; i < nseg; i++) {
+        const gbxq_segment& s = segs[i];
+        const int rc = validate(M, s.N, K, s.bits, s.group_size, dtype);
+        if (rc != GBXQ_OK) return rc;
+        if (M == 0 || s.N == 0) continue;
+        if (!x || !s.qweight || !s.scales || !s.biases || !s.y) return GBXQ_ENULL;
+        if (((uintptr_t)x | (uintptr_t)s.y | (uintptr_t)s.scales | (uintptr_t)s.biases | (uintptr_t)s.bias) & (esz - 1))
+            return GBXQ_EALIGN;
+        if ((uintptr_t)s.qweight & 3) return GBXQ_EALIGN;
+    }
+    if (M == 0) return GBXQ_OK;
+    if (dtype == GBXQ_BF16 && nseg >= 2 && nseg <= GBXQ_MAX_SEGMENTS) {
+        const int rc = launch_mmv8_grouped(segs, nseg, x, M, K, (cudaStream_t)stream);
+        if (rc != GBXQ_EUNSUPPORTED) return rc;
+    }
+    for (int i = 0; i < nseg; i++) {
+        const gbxq_segment& s = segs[i];
+        const int rc = gbxq_qmm_ex(x, s.qweight, s.scales, s.biases, s.bias, s.y, M, s.N, K, s.bits, s.group_size, dtype,
+                                   GBXQ_KERNEL_AUTO, nullptr, 0, stream);
+        if (rc != GBXQ_OK) return rc;
+    }
+    return GBXQ_OK;
+}
+
 int gbxq_dequantize(const uint32_t* qweight, const void* scales, const void* biases, void* w_out, int64_t N,
                     int64_t K, int bits, int group_size, int dtype, void* stream) {
     const int rc = validate(0, N, K, bits, group_size, dtype);

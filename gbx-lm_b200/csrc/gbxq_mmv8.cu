@@ -24,479 +24,19 @@
 //   * y += scale[n,g] * 2^(e-13) * T(n,g)  per group, in fp32;  biases: y += sum_g bias[n,g] * sum(x over g),
 //     a [rows x groups] dot product against per-lane stationary group sums.
 //   * Streaming, ring, PDL, deterministic shared-memory reduction and epilogue are those of gbxq_mmv.cu.
-#include "gbxq_common.cuh"
+#include "gbxq_mmv8_body.cuh"
 
 namespace gbxq {
 
+using namespace mmv8;
+
 namespace {
-
-constexpr int kCW = 8;                        // consumer warps
-constexpr int kThreads = (kCW + 1) * 32;      // + producer warp
-constexpr int kMaxStages = 4;
-#ifndef GBXQ_MMV8_MINCTAS
-#define GBXQ_MMV8_MINCTAS 2
-#endif
-constexpr int kMinCtas = GBXQ_MMV8_MINCTAS;    // register cap 112; a cap of 72 (3 CTAs / SM) measured 15 % slower
-constexpr int S = 4;                          // group slices per chunk column (= 8 columns / 2 digits)
-constexpr int W = 4;                          // weight rows per MMA set (= 16 A rows / S)
-
-__device__ __forceinline__ void imma16832(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
-                                          uint32_t b1, const int (&c)[4]) {
-    asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
-        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
-        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]));
-}
-__device__ __forceinline__ unsigned long long gtime() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-#define STAMP(i)                                                                   \
-    do {                                                                           \
-        if (p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[i] = gtime(); \
-    } while (0)
-__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
-template <int NWORD> __device__ __forceinline__ void lds_words(const uint8_t* addr, uint32_t (&w)[NWORD]) {
-    if constexpr (NWORD == 1) {
-        w[0] = *reinterpret_cast<const uint32_t*>(addr);
-    } else if constexpr (NWORD == 2) {
-        const uint2 v = *reinterpret_cast<const uint2*>(addr);
-        w[0] = v.x; w[1] = v.y;
-    } else {
-#pragma unroll
-        for (int i = 0; i < NWORD / 4; i++) {
-            const uint4 v = *reinterpret_cast<const uint4*>(addr + 16 * i);
-            w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
-        }
-    }
-}
-__device__ __forceinline__ float lds_bf16(const uint8_t* addr) {
-    return __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(addr)) << 16);
-}
-
-// ---- packing geometry.  A thread chunk = CQ = group_size/4 codes of one (row, group).  NMMA MMAs per chunk and
-//      accumulator class; MMA u of class c takes A registers areg(c, u, 0) [k-slots 4t..4t+3] and areg(c, u, 1)
-//      [k-slots 16+4t..]; byte i of such a register is code code_of(c, u, half, i) of the chunk.
-template <int BITS, int CQ> struct Geo {
-    static constexpr int NWORD = CQ * BITS / 32;
-    static constexpr int NCLASS = BITS == 8 ? 1 : 2;
-    static constexpr int NREG = CQ / 4;                    // A registers (4 codes each) per chunk
-    static constexpr int NMMA = (NREG / NCLASS + 1) / 2;   // k32 MMAs per class (a lone register pairs with zero)
-    static constexpr bool HALF = (NREG / NCLASS) % 2 == 1; // last MMA of a class has no second register
-    static constexpr int CMUL = BITS == 8 ? 1 : (BITS == 4 ? 16 : 4);  // T = CMUL * D0 + D1; scale / CMUL
-    __host__ __device__ static constexpr int code_of(int c, int u, int half, int i) {
-        if (BITS == 8) return 8 * u + 4 * half + i;                       // word 2u+half, byte i
-        if (BITS == 4) return 16 * u + 8 * half + 2 * i + c;              // word 2u+half, nibble 2i+c
-        return 16 * u + 4 * i + 2 * half + c;                             // 2-bit: word u, field 4i + 2*half + c
-    }
-};
-
-template <int BITS, int CQ>
-__device__ __forceinline__ uint32_t areg(const uint32_t (&w)[Geo<BITS, CQ>::NWORD], int c, int u, int half) {
-    if constexpr (BITS == 8) {
-        return w[2 * u + half];
-    } else if constexpr (BITS == 4) {
-        const uint32_t word = w[2 * u + half];
-        return c == 0 ? (word & 0x0f0f0f0fu) : (word & 0xf0f0f0f0u);
-    } else {
-        const uint32_t word = half == 0 ? w[u] : (w[u] >> 4);
-        return c == 0 ? (word & 0x03030303u) : (word & 0x0c0c0c0cu);
-    }
-}
-
-struct Mmv8Params {
-    const __nv_bfloat16* x;
-    const uint8_t* w;
-    const uint16_t* scales;
-    const uint16_t* biases;
-    const __nv_bfloat16* bias;
-    __nv_bfloat16* y;
-    int64_t N, K;
-    int M;                // rows of x in this launch (<= MT)
-    int G;                // groups per row
-    uint32_t row_bytes;
-    int nch;              // chunk columns per row (a chunk column = S groups)
-    int cw, rg;           // warp grid: cw chunk columns x rg row groups (cw * rg <= 8)
-    int tr;               // rows per ring stage (= rg * R)
-    int stages;
-    uint32_t slot_bytes;  // ring slot size
-    uint32_t sb_off;      // offset of the scales inside a slot (biases follow at sb_off + tr*G*2)
-    int early_weights;    // 1: weights are immutable while the call is in flight -> stream them before griddepcontrol.wait
-    unsigned long long* dbg;  // optional timeline (gbxq_debug_timeline): 8 globaltimer stamps per launch, CTA 0 / warp 0
-    int rows_base, rows_rem;  // CTA b owns rows_base + (b < rows_rem) rows starting at b*rows_base + min(b, rows_rem)
-    int spr0, spr1;           // rows per stage for CTAs with rows_base / rows_base+1 rows (balanced, whole MMA sets)
-};
 
 // BITS, GS = group size, MT = tokens (1, 2, 4), CPW = chunk columns per warp, R = rows per warp and stage (4 or 8)
 template <int BITS, int GS, int MT, int CPW, int R>
 __global__ void __launch_bounds__(kThreads, kMinCtas) mmv8_kernel(const Mmv8Params p) {
-    constexpr int CQ = GS / 4;
-    using GE = Geo<BITS, CQ>;
-    constexpr int NWORD = GE::NWORD, NCLASS = GE::NCLASS, NMMA = GE::NMMA;
-    constexpr int TB = CQ * BITS / 8;        // bytes per thread chunk
-    constexpr int NSET = R / W;
-    constexpr int KSTEP_B = S * 4 * TB;      // bytes of one weight row inside a chunk column
-    constexpr int LPR = 32 / R;              // lanes per row in the bias dot product
-    constexpr int NGL = (CPW * S + LPR - 1) / LPR;
-    static_assert(R % W == 0 && NWORD >= 1, "geometry");
-
     extern __shared__ __align__(1024) uint8_t smem[];
-    // layout: [ring stages * slot][full/empty barriers (2*kMaxStages)][xsc kCW * CPW*S*MT f32][ysum rows * 2cw * MT f32]
-    uint8_t* ring = smem;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + (size_t)p.stages * p.slot_bytes);
-    uint64_t* empty_bar = full_bar + kMaxStages;
-    float* xsc = reinterpret_cast<float*>(empty_bar + kMaxStages);
-    float* ysum = xsc + kCW * (CPW * S * MT);
-
-    STAMP(0);
-    const int bid = (int)blockIdx.x;
-    const bool extra = bid < p.rows_rem;
-    const int64_t r0 = (int64_t)bid * p.rows_base + (extra ? bid : p.rows_rem);
-    const int rows = p.rows_base + (extra ? 1 : 0);
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int nstg = p.stages;
-    const int spr = extra ? p.spr1 : p.spr0;
-    const int active_warps = p.cw * p.rg;
-    const int slots = 2 * p.cw;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < nstg; s++) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], active_warps);
-        }
-        fence_mbar_init();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) griddep_launch();  // the next kernel of the stream may become resident now
-
-    if (warp == kCW) {
-        // ===================== producer warp: one elected lane drives the TMA engine =====================
-        if (lane == 0 && rows > 0) {
-            if (!p.early_weights) griddep_wait();
-            const uint8_t* wsrc = p.w + (uint64_t)r0 * p.row_bytes;
-            const uint32_t g2 = (uint32_t)p.G * 2u;
-            int s = 0;
-            uint32_t phase = 0;
-            for (int ra = 0; ra < rows; ra += spr) {
-                mbar_wait(&empty_bar[s], phase ^ 1u);
-                int nr = rows - ra;
-                if (nr > spr) nr = spr;
-                const uint32_t wbytes = (uint32_t)nr * p.row_bytes;
-                const uint32_t sbytes = (uint32_t)nr * g2;
-                uint8_t* slot = ring + (size_t)s * p.slot_bytes;
-                mbar_arrive_expect_tx(&full_bar[s], wbytes + 2u * sbytes);
-                bulk_g2s(slot, wsrc + (uint64_t)ra * p.row_bytes, wbytes, &full_bar[s]);
-                const uint64_t soff = (uint64_t)(r0 + ra) * g2;
-                bulk_g2s(slot + p.sb_off, reinterpret_cast<const uint8_t*>(p.scales) + soff, sbytes, &full_bar[s]);
-                bulk_g2s(slot + p.sb_off + (uint32_t)p.tr * g2, reinterpret_cast<const uint8_t*>(p.biases) + soff, sbytes,
-                         &full_bar[s]);
-                if (++s == nstg) {
-                    s = 0;
-                    phase ^= 1u;
-                }
-            }
-        }
-    } else if (warp < active_warps && rows > 0) {
-        // ===================== consumer warps =====================
-        const int cwi = warp % p.cw;  // chunk column
-        const int rgi = warp / p.cw;  // row group
-        const int g = lane >> 2, t = lane & 3;
-        // lane -> (weight row inside the set, group slice) of the two A-row parts (MMA rows g and g+8)
-        const int wrow = g >> 1;
-        const int sA = g & 1, sB = 2 + (g & 1);
-        // lane as B-column holder: column g = (slice g>>1, digit g&1)
-        const int bsl = g >> 1, bdig = g & 1;
-        // accumulators c0,c1 (c2,c3) = columns 2t, 2t+1 = (slice t, digits 0/1): meaningful for part A iff t == sA,
-        // for part B iff t == sB; this lane's meaningful part (if any) multiplies group slice t
-        const bool mean = (t & 1) == (g & 1);
-
-        griddep_wait();  // x (and y) belong to the previous kernels of the stream
-        STAMP(1);
-
-        // ---- stationary operands: digit fragments of the activations, per-group power-of-two factors, group sums
-        uint32_t bfr[MT][CPW][NCLASS][NMMA][2];
-        float pw[MT][CPW];  // 2^(e-13) / CMUL of group slice t of chunk column j (the slice this lane's accumulators need)
-        float* myx = xsc + warp * (CPW * S * MT);
-#pragma unroll
-        for (int m = 0; m < MT; m++) {
-#pragma unroll
-            for (int j = 0; j < CPW; j++) {
-                const int c = cwi + j * p.cw;
-                const bool ld = (c < p.nch) && (m < p.M);
-                const int64_t k0 = ((int64_t)c * S + bsl) * GS + t * CQ;
-                uint32_t n32[CQ / 2];  // n32[i] = codes (2i, 2i+1) of the chunk, natural order
-                const uint4* src = reinterpret_cast<const uint4*>(p.x + (size_t)m * p.K + k0);
-#pragma unroll
-                for (int v = 0; v < CQ / 8; v++) {
-                    const uint4 q = ld ? __ldg(src + v) : make_uint4(0u, 0u, 0u, 0u);
-                    n32[4 * v + 0] = q.x; n32[4 * v + 1] = q.y; n32[4 * v + 2] = q.z; n32[4 * v + 3] = q.w;
-                }
-                // |x| maximum of the chunk as packed 16-bit lanes; sum of x in fp32
-                uint32_t amax2 = 0;
-                float sx = 0.f;
-                float xf[CQ];
-#pragma unroll
-                for (int i = 0; i < CQ / 2; i++) {
-                    amax2 = __vmaxu2(amax2, n32[i] & 0x7fff7fffu);
-                    xf[2 * i] = __uint_as_float(n32[i] << 16);
-                    xf[2 * i + 1] = __uint_as_float(n32[i] & 0xffff0000u);
-                    sx += xf[2 * i];
-                    sx += xf[2 * i + 1];
-                }
-                uint32_t amax = max(amax2 & 0xffffu, amax2 >> 16);  // bf16 bits of the largest |x|
-                sx += __shfl_xor_sync(0xffffffffu, sx, 1);
-                sx += __shfl_xor_sync(0xffffffffu, sx, 2);
-                amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-                amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-                if (t == 0 && bdig == 0) myx[(j * S + bsl) * MT + m] = sx;  // true sum of x over (group, token)
-                // block exponent of the group: |x| < 2^(e+1); m = round(x * 2^(13-e)), |m| < 2^14
-                int e = (int)(amax >> 7) - 127;
-                if (e < -100) e = -100;  // zeros / denormal groups: any finite scale works
-                const bool bad = (amax >> 7) == 255u;  // inf / nan in the group: poison the group's factor
-                const float up = __uint_as_float((uint32_t)(127 + 13 - e) << 23);        // 2^(13-e)
-                const float dn = __uint_as_float((uint32_t)(127 - 13 + e) << 23);        // 2^(e-13)
-                // the factor this lane needs is the one of slice t, held by the lanes with g>>1 == t
-                const float dn_t = __shfl_sync(0xffffffffu, bad ? __uint_as_float(0x7fc00000u) : dn, t << 3);
-                pw[m][j] = dn_t * (1.0f / GE::CMUL);
-                // balanced base-256 digits: lo = low byte of m (as s8), hi = (m + 128) >> 8.  1.5*2^23 + m has m's two's
-                // complement in its low mantissa bits; adding 128 there puts hi into byte 1: each lane takes byte `bdig`.
-                const float magic = bdig ? 12583040.0f : 12582912.0f;  // 1.5*2^23 (+ 128)
-                const uint32_t sel2 = bdig ? 0x0051u : 0x0040u;        // PRMT: byte bdig of two words -> low half
-                uint32_t pr[CQ / 2];  // pr[i] = digit bytes of codes (2i, 2i+1) in the low half
-#pragma unroll
-                for (int i = 0; i < CQ / 2; i++) {
-                    const uint32_t m0 = __float_as_uint(fmaf(xf[2 * i], up, magic));
-                    const uint32_t m1 = __float_as_uint(fmaf(xf[2 * i + 1], up, magic));
-                    pr[i] = __byte_perm(m0, m1, sel2);
-                }
-#pragma unroll
-                for (int c2 = 0; c2 < NCLASS; c2++)
-#pragma unroll
-                    for (int u = 0; u < NMMA; u++)
-#pragma unroll
-                        for (int h = 0; h < 2; h++) {
-                            uint32_t r = 0;
-                            if (!(GE::HALF && u == NMMA - 1 && h == 1)) {
-                                // bytes i = 0..3 <- codes code_of(c2,u,h,i); code k sits in byte (k&1) of pr[k>>1]
-                                const int k0c = GE::code_of(c2, u, h, 0), k1c = GE::code_of(c2, u, h, 1);
-                                const int k2c = GE::code_of(c2, u, h, 2), k3c = GE::code_of(c2, u, h, 3);
-                                const uint32_t lo2 = __byte_perm(pr[k0c >> 1], pr[k1c >> 1], (k0c & 1) | ((4 + (k1c & 1)) << 4));
-                                const uint32_t hi2 = __byte_perm(pr[k2c >> 1], pr[k3c >> 1], (k2c & 1) | ((4 + (k3c & 1)) << 4));
-                                r = __byte_perm(lo2, hi2, 0x5410);
-                            }
-                            bfr[m][j][c2][u][h] = r;
-                        }
-            }
-        }
-        __syncwarp();
-        const int brow = lane / LPR, bq = lane % LPR;
-        const uint32_t g2 = (uint32_t)p.G * 2u;
-        const int lrow0 = rgi * R;
-        int ncl = 0;  // live chunk columns of this warp (warp-uniform)
-#pragma unroll
-        for (int j = 0; j < CPW; j++) ncl += (cwi + j * p.cw < p.nch) ? 1 : 0;
-        float xg[NGL][MT];
-        uint32_t bofs[NGL];  // byte offset of the lane's bias entries inside a stage (dead entries: x sum = 0, offset 0)
-#pragma unroll
-        for (int i = 0; i < NGL; i++) {
-            const int idx = bq * NGL + i;
-            const int c = cwi + (idx / S) * p.cw;
-            const bool on = idx < CPW * S && c < p.nch;
-#pragma unroll
-            for (int m = 0; m < MT; m++) xg[i][m] = on ? myx[idx * MT + m] : 0.f;
-            bofs[i] = (uint32_t)(p.tr + lrow0 + brow) * g2 + (on ? (uint32_t)(c * S + idx % S) * 2u : 0u);
-        }
-
-        const uint32_t colstride = (uint32_t)p.cw * KSTEP_B;
-        const uint32_t offA = (uint32_t)wrow * p.row_bytes + (uint32_t)cwi * KSTEP_B + (uint32_t)(sA * 4 + t) * TB;
-        const uint32_t offB = (uint32_t)wrow * p.row_bytes + (uint32_t)cwi * KSTEP_B + (uint32_t)(sB * 4 + t) * TB;
-        // scale of the slice this lane's accumulators belong to (slice t of the chunk column), row = wrow
-        const uint32_t sofT = (uint32_t)wrow * g2 + (uint32_t)(cwi * S + t) * 2u;
-        const uint32_t sstride = (uint32_t)p.cw * S * 2u;
-
-        STAMP(2);
-        int s = 0;
-        uint32_t phase = 0;
-        for (int ra = 0; ra < rows; ra += spr) {
-            int nr = rows - ra;
-            if (nr > spr) nr = spr;
-            mbar_wait(&full_bar[s], phase);
-            if (ra == 0) STAMP(3);
-            const uint8_t* slot = ring + (size_t)s * p.slot_bytes;
-            const uint8_t* sslot = slot + p.sb_off;
-
-            float yacc[NSET][MT];
-            // one (set, chunk column) unit: 2 LDS of packed words, mask into u8 A registers, NCLASS*NMMA IMMAs per token on the
-            // group's accumulators, recombine classes and digits in int32, one I2F, fold with scale * 2^(e-13).
-            // Sets past `nr` read stale shared memory; their rows are dropped at the write.
-            auto unit = [&](int q, int j) {
-                const uint8_t* rbase = slot + (uint32_t)(lrow0 + q * W) * p.row_bytes + j * colstride;
-                uint32_t wa[NWORD], wb[NWORD];
-                lds_words<NWORD>(rbase + offA, wa);
-                lds_words<NWORD>(rbase + offB, wb);
-                const float sc = lds_bf16(sslot + (uint32_t)(lrow0 + q * W) * g2 + j * sstride + sofT);
-                const int kZero4[4] = {0, 0, 0, 0};
-                int T[MT][2];  // [token][part]: 256 * hi + lo of the meaningful part's group
-#pragma unroll
-                for (int m = 0; m < MT; m++) {
-                    int d[NCLASS][4];
-#pragma unroll
-                    for (int c = 0; c < NCLASS; c++) {
-#pragma unroll
-                        for (int u = 0; u < NMMA; u++) {
-                            const bool lone = GE::HALF && u == NMMA - 1;
-                            const uint32_t a0 = areg<BITS, CQ>(wa, c, u, 0), a1 = areg<BITS, CQ>(wb, c, u, 0);
-                            const uint32_t a2 = lone ? 0u : areg<BITS, CQ>(wa, c, u, 1), a3 = lone ? 0u : areg<BITS, CQ>(wb, c, u, 1);
-                            if (u == 0) imma16832(d[c], a0, a1, a2, a3, bfr[m][j][c][u][0], bfr[m][j][c][u][1], kZero4);
-                            else imma16832(d[c], a0, a1, a2, a3, bfr[m][j][c][u][0], bfr[m][j][c][u][1], d[c]);
-                        }
-                    }
-#pragma unroll
-                    for (int e = 0; e < 4; e++)
-                        if constexpr (NCLASS == 2) d[0][e] = d[0][e] * GE::CMUL + d[1][e];
-                    T[m][0] = d[0][1] * 256 + d[0][0];
-                    T[m][1] = d[0][3] * 256 + d[0][2];
-                }
-#pragma unroll
-                for (int m = 0; m < MT; m++) {
-                    const int tt = (t & 2) ? T[m][1] : T[m][0];  // the part whose slice is t (garbage where !mean: dropped below)
-                    yacc[q][m] = fmaf(sc * pw[m][j], (float)tt, yacc[q][m]);
-                }
-            };
-#pragma unroll
-            for (int q = 0; q < NSET; q++)
-#pragma unroll
-                for (int m = 0; m < MT; m++) yacc[q][m] = 0.f;
-            if (ncl == CPW) {
-                // fast path: straight-line code, the NSET * CPW units are independent chains the scheduler interleaves
-#pragma unroll
-                for (int q = 0; q < NSET; q++)
-#pragma unroll
-                    for (int j = 0; j < CPW; j++) unit(q, j);
-            } else {
-#pragma unroll
-                for (int q = 0; q < NSET; q++)
-#pragma unroll
-                    for (int j = 0; j < CPW; j++)
-                        if (j < ncl) unit(q, j);
-            }
-            // ---- biases: sum_g bias * sum(x over g), a rows x groups dot product against per-lane stationary group sums
-            float bacc[MT];
-#pragma unroll
-            for (int m = 0; m < MT; m++) bacc[m] = 0.f;
-#pragma unroll
-            for (int i = 0; i < NGL; i++) {
-                const float bv = lds_bf16(sslot + bofs[i]);
-#pragma unroll
-                for (int m = 0; m < MT; m++) bacc[m] = fmaf(bv, xg[i][m], bacc[m]);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[s]);  // slot free: all of this warp's shared-memory reads are done
-            if (++s == nstg) {
-                s = 0;
-                phase ^= 1u;
-            }
-#pragma unroll
-            for (int m = 0; m < MT; m++) {
-#pragma unroll
-                for (int o = LPR / 2; o > 0; o >>= 1) bacc[m] += __shfl_xor_sync(0xffffffffu, bacc[m], o);
-            }
-            if (bq == 0 && lrow0 + brow < nr) {
-#pragma unroll
-                for (int m = 0; m < MT; m++) ysum[((ra + lrow0 + brow) * slots + p.cw + cwi) * MT + m] = bacc[m];
-            }
-            // ---- keep the meaningful accumulators; the 8 lanes (g&1, t) of a weight row are folded by a butterfly
-#pragma unroll
-            for (int q = 0; q < NSET; q++) {
-#pragma unroll
-                for (int m = 0; m < MT; m++) {
-                    float v = mean ? yacc[q][m] : 0.f;
-                    v += __shfl_xor_sync(0xffffffffu, v, 4);
-                    v += __shfl_xor_sync(0xffffffffu, v, 2);
-                    v += __shfl_xor_sync(0xffffffffu, v, 1);
-                    const int lr = lrow0 + q * W + (lane >> 3);
-                    if ((lane & 7) == 0 && lr < nr) ysum[((ra + lr) * slots + cwi) * MT + m] = v;
-                }
-            }
-        }
-    }
-    STAMP(4);
-    __syncthreads();
-    STAMP(5);
-    griddep_wait();  // every thread stores y below (returns at once when a consumer warp has already waited)
-    // ---- epilogue: one rounding to bf16, optional bias as a second rounded add, coalesced store
-    for (int i = threadIdx.x; i < rows * MT; i += kThreads) {
-        const int m = i / rows, r = i - m * rows;
-        if (m < p.M) {
-            float tot = 0.f;
-            for (int c = 0; c < slots; c++) tot += ysum[(r * slots + c) * MT + m];
-            float v = __bfloat162float(__float2bfloat16_rn(tot));
-            if (p.bias != nullptr) v = __fadd_rn(v, __bfloat162float(p.bias[r0 + r]));
-            p.y[(size_t)m * p.N + r0 + r] = __float2bfloat16_rn(v);
-        }
-    }
-    STAMP(6);
-}
-
-// ------------------------------------------------------------------------------------------ host side
-struct Plan {
-    bool ok;
-    int mt, cpw, R, nch, cw, rg, tr, stages, grid;
-    uint32_t slot_bytes, sb_off;
-    size_t smem;
-};
-
-int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v ? atoi(v) : dflt;
-}
-
-Plan make_plan(int64_t M, int64_t N, int64_t K, int bits, int gs) {
-    Plan pl{};
-    if (!(bits == 2 || bits == 4 || bits == 8) || M < 1 || M > 4 || N < 1) return pl;
-    if (bits == 2 && gs == 32) return pl;  // a thread chunk would be half a word
-    const int64_t G = K / gs;
-    if (G % 8) return pl;  // S | G, and 16-byte rows of scales for the bulk copies
-    const int64_t row_bytes = K * bits / 8;
-    pl.mt = M == 1 ? 1 : (M == 2 ? 2 : 4);
-    pl.nch = (int)(G / S);
-    static const int force_cpw = env_int("GBXQ_MMV8_CPW", 0);
-    static const int grid_mult = env_int("GBXQ_MMV8_GRID_MULT", 2);
-    static const int stage_kb = env_int("GBXQ_MMV8_STAGE_KB", 32);
-    static const int ring_kb = env_int("GBXQ_MMV8_RING_KB", 96);
-    // chunk columns per warp: the smallest power of two that covers the row with 8 warps, but at least 2 (two
-    // independent MMA chains per set) when the row has 8 columns or more
-    pl.cpw = pl.nch >= 8 ? 2 : 1;
-    while ((pl.nch + pl.cpw - 1) / pl.cpw > kCW && pl.cpw < 8) pl.cpw *= 2;
-    if (force_cpw) pl.cpw = force_cpw;
-    if (!(pl.cpw == 1 || pl.cpw == 2 || pl.cpw == 4 || pl.cpw == 8)) return pl;
-    pl.cw = (pl.nch + pl.cpw - 1) / pl.cpw;
-    if (pl.cw > kCW) return pl;
-    pl.rg = kCW / pl.cw;
-    pl.R = pl.cpw <= 2 ? 8 : 4;
-    if ((int64_t)pl.R * row_bytes > (int64_t)stage_kb * 1024) pl.R = 4;
-    if ((int64_t)pl.R * row_bytes > (int64_t)stage_kb * 1024) return pl;
-    while (pl.rg > 1 && (int64_t)pl.rg * pl.R * row_bytes > (int64_t)stage_kb * 1024 / 2) pl.rg--;
-    pl.tr = pl.rg * pl.R;
-    const uint32_t wpart = (uint32_t)(((int64_t)pl.tr * row_bytes + 127) & ~(int64_t)127);
-    pl.sb_off = wpart;
-    pl.slot_bytes = wpart + (uint32_t)((2 * (int64_t)pl.tr * G * 2 + 127) & ~(int64_t)127);
-    pl.stages = kMaxStages;
-    while (pl.stages > 2 && (size_t)pl.stages * pl.slot_bytes > (size_t)ring_kb * 1024) pl.stages--;
-    int grid = device_sm_count() * grid_mult;
-    const int64_t min_rows = pl.tr;
-    if ((int64_t)grid * min_rows > N) grid = (int)((N + min_rows - 1) / min_rows);
-    if (grid < 1) grid = 1;
-    pl.grid = grid;
-    const int64_t rows_max = (N + grid - 1) / grid;
-    pl.smem = (size_t)pl.stages * pl.slot_bytes + 2 * kMaxStages * 8 + (size_t)kCW * pl.cpw * S * pl.mt * 4 +
-              (size_t)rows_max * 2 * pl.cw * pl.mt * 4 + 16;
-    if (pl.smem > 110 * 1024) return pl;
-    pl.ok = true;
-    return pl;
+    mmv8_body<BITS, GS, MT, CPW, R>(p, (int)blockIdx.x, smem);
 }
 
 template <int BITS, int GS, int MT, int CPW, int R>
@@ -578,40 +118,12 @@ int launch_mmv8(const void* x, const uint32_t* w, const void* s, const void* b, 
     if (((uintptr_t)s | (uintptr_t)b) & 15) return GBXQ_EUNSUPPORTED;
     const Plan pl = make_plan(M, N, K, bits, gs);
     if (!pl.ok) return GBXQ_EUNSUPPORTED;
-    Mmv8Params p{};
-    p.x = reinterpret_cast<const __nv_bfloat16*>(x);
-    p.w = reinterpret_cast<const uint8_t*>(w);
-    p.scales = reinterpret_cast<const uint16_t*>(s);
-    p.biases = reinterpret_cast<const uint16_t*>(b);
-    p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
-    p.y = reinterpret_cast<__nv_bfloat16*>(y);
-    p.N = N;
-    p.K = K;
-    p.M = (int)M;
-    p.G = (int)(K / gs);
-    p.row_bytes = (uint32_t)(K * bits / 8);
-    p.nch = pl.nch;
-    p.cw = pl.cw;
-    p.rg = pl.rg;
-    p.tr = pl.tr;
-    p.stages = pl.stages;
-    p.slot_bytes = pl.slot_bytes;
-    p.sb_off = pl.sb_off;
-    p.early_weights = mmv_get_pdl_mode() >= 2 ? 1 : 0;
+    Mmv8Params p = make_params(pl, x, w, s, b, bias, y, M, N, K, bits, gs, mmv_get_pdl_mode() >= 2 ? 1 : 0);
     if (g_dbg != nullptr && g_dbg_left > 0) {
         p.dbg = g_dbg;
         g_dbg += 8;
         g_dbg_left--;
     }
-    p.rows_base = (int)(N / pl.grid);
-    p.rows_rem = (int)(N % pl.grid);
-    auto spr_of = [&](int rows) {
-        if (rows <= 0) return W;
-        const int ns = (rows + pl.tr - 1) / pl.tr;
-        return (((rows + ns - 1) / ns + W - 1) / W) * W;  // balanced stages, whole MMA sets
-    };
-    p.spr0 = spr_of(p.rows_base);
-    p.spr1 = spr_of(p.rows_base + 1);
     switch (bits * 1000 + gs) {
         case 4064: return launch_mt<4, 64>(p, pl, st);
         case 4128: return launch_mt<4, 128>(p, pl, st);

@@ -11,7 +11,7 @@ propagation, CUDA-graph capturable: the library only enqueues on the current str
 CUDA only -- there is deliberately no CPU implementation."""
 from __future__ import annotations
 
-from typing import Optional
+from typing import List, Optional, Sequence
 
 import torch
 
@@ -128,6 +128,57 @@ def _(x, w, scales, biases, bias, group_size, bits, kernel):
     return x.new_empty((*x.shape[:-1], w.shape[0]))
 
 
+@torch.library.custom_op("gbxq::qmm_grouped", mutates_args=(), device_types="cuda")
+def _qmm_grouped_op(
+    x: torch.Tensor,
+    ws: List[torch.Tensor],
+    scales: List[torch.Tensor],
+    biases: List[torch.Tensor],
+    bias: List[Optional[torch.Tensor]],
+    group_sizes: List[int],
+    bits: List[int],
+) -> List[torch.Tensor]:
+    nseg = len(ws)
+    if not (len(scales) == len(biases) == len(bias) == len(group_sizes) == len(bits) == nseg):
+        raise ValueError("[quantized_matmul_grouped] per-segment lists must have the same length")
+    _require_cuda(x, *ws, *scales, *biases, *bias)
+    dt = _dt(x)
+    k = x.shape[-1]
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, k)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    m = x2.shape[0]
+    segs = (_lib.Segment * max(nseg, 1))()
+    outs, keep = [], []
+    for i in range(nseg):
+        _as_u32_ptr_tensor(ws[i])
+        n, _ = _check_shapes(ws[i], scales[i], biases[i], group_sizes[i], bits[i], k)
+        if x.dtype != scales[i].dtype:
+            raise ValueError(f"[quantized_matmul_grouped] x ({x.dtype}) and scales ({scales[i].dtype}) must share a dtype")
+        w, s, b = ws[i].contiguous(), scales[i].contiguous(), biases[i].contiguous()
+        bi = bias[i]
+        if bi is not None:
+            if bi.dtype != x.dtype or bi.numel() != n:
+                raise ValueError("[quantized_matmul_grouped] bias must be [N] in the activation dtype")
+            bi = bi.contiguous()
+        y = torch.empty((m, n), dtype=x.dtype, device=x.device)
+        keep.append((w, s, b, bi))
+        outs.append(y)
+        segs[i] = _lib.Segment(w.data_ptr(), s.data_ptr(), b.data_ptr(), bi.data_ptr() if bi is not None else None,
+                               y.data_ptr(), n, bits[i], group_sizes[i])
+    with torch.cuda.device(x.device):
+        st = torch.cuda.current_stream().cuda_stream
+        rc = _lib.get().gbxq_qmm_grouped(segs, nseg, x2.data_ptr(), m, k, dt, st)
+    _lib.check(rc, "gbxq_qmm_grouped")
+    return [y.reshape(*lead, y.shape[-1]) for y in outs]
+
+
+@_qmm_grouped_op.register_fake
+def _(x, ws, scales, biases, bias, group_sizes, bits):
+    return [x.new_empty((*x.shape[:-1], w.shape[0])) for w in ws]
+
+
 @torch.library.custom_op("gbxq::dequantize", mutates_args=(), device_types="cuda")
 def _dequantize_op(w: torch.Tensor, scales: torch.Tensor, biases: torch.Tensor, group_size: int, bits: int) -> torch.Tensor:
     _require_cuda(w, scales, biases)
@@ -168,6 +219,20 @@ def quantized_matmul(
     if not transpose:
         raise NotImplementedError("quantized_matmul(transpose=False) is outside the QuantizedLinear path")
     return _qmm_op(x, w, scales, biases, bias, int(group_size), int(bits), _KERNELS[kernel])
+
+
+def quantized_matmul_grouped(x: torch.Tensor, layers: Sequence) -> List[torch.Tensor]:
+    """The projections that read the same activations -- q_proj|k_proj|v_proj (gbx_lm/models/qllama.py:76) and
+    gate_proj|up_proj (qllama.py:115) -- as ONE call: `layers` are QuantizedLinear-like objects (attributes
+    qweight/scales/zeros/bias/group_size/bits).  Results are identical to calling each layer on x; at decode
+    batch sizes (M <= 4) with a common group size the work is a single kernel launch (gbxq_qmm_grouped)."""
+    layers = list(layers)
+    if len(layers) > _lib.MAX_SEGMENTS:
+        raise ValueError(f"[quantized_matmul_grouped] at most {_lib.MAX_SEGMENTS} projections per call")
+    return _qmm_grouped_op(
+        x, [l.qweight for l in layers], [l.scales for l in layers], [l.zeros for l in layers],
+        [getattr(l, "bias", None) for l in layers], [int(l.group_size) for l in layers], [int(l.bits) for l in layers],
+    )
 
 
 def dequantize(w: torch.Tensor, scales: torch.Tensor, biases: torch.Tensor, group_size: int = 64, bits: int = 4) -> torch.Tensor:

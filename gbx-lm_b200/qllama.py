@@ -21,6 +21,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from . import ops
 from .quantized_linear import QuantizedLinear
 from .tp import TPContext
 
@@ -147,7 +148,8 @@ class Attention(nn.Module):  # gbx_lm/models/qllama.py:39-96
 
     def forward(self, x, positions, cache: Optional[KVCache], attend_len: Optional[int]):
         B, L, _ = x.shape
-        q, k, v = self.q_proj(x), self.k_proj(x), self.v_proj(x)
+        # one grouped launch for the three projections of x (ref qllama.py:76 calls them back to back)
+        q, k, v = ops.quantized_matmul_grouped(x, (self.q_proj, self.k_proj, self.v_proj))
         q = q.view(B, L, self.n_heads, -1).transpose(1, 2)
         k = k.view(B, L, self.n_kv_heads, -1).transpose(1, 2)
         v = v.view(B, L, self.n_kv_heads, -1).transpose(1, 2)
@@ -180,7 +182,8 @@ class MLP(nn.Module):  # gbx_lm/models/qllama.py:99-115
         self.up_proj = QuantizedLinear(dim, hidden_dim // tp.world, bias=mlp_bias)
 
     def forward(self, x):
-        return self.tp.all_reduce(self.down_proj(F.silu(self.gate_proj(x)) * self.up_proj(x)))
+        gate, up = ops.quantized_matmul_grouped(x, (self.gate_proj, self.up_proj))  # ref qllama.py:115
+        return self.tp.all_reduce(self.down_proj(F.silu(gate) * up))
 
 
 class TransformerBlock(nn.Module):  # gbx_lm/models/qllama.py:118-141

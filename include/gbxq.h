@@ -111,6 +111,29 @@ int gbxq_qmm_ex(const void* x, const uint32_t* qweight, const void* scales, cons
                 int group_size, int dtype, int kernel, void* workspace, size_t workspace_bytes,
                 void* stream);
 
+/*
+ * Grouped launch: nseg (<= GBXQ_MAX_SEGMENTS) quantized projections that read the SAME activations x[M,K], each
+ * with its own weights, bit width, optional bias and output -- the back-to-back q_proj/k_proj/v_proj and
+ * gate_proj/up_proj calls of the reference (gbx_lm/models/qllama.py:76,115; gbx_lm/models/qqwen2.py:66,94), whose
+ * bit widths differ per projection in layer-mix checkpoints (quantized_linear_gba.py:258-272).
+ * Semantics are exactly those of nseg gbxq_qmm calls (y_s[M,N_s] = x . dequant(W_s)^T (+ bias_s)), results are
+ * identical to them; when M <= 4 and the segments share K and group_size the work is ONE kernel launch, otherwise
+ * the call enqueues one launch per segment.  `segs` is a HOST array read before the call returns.
+ */
+#define GBXQ_MAX_SEGMENTS 4
+typedef struct gbxq_segment {
+    const uint32_t* qweight; /* [N, K*bits/32] */
+    const void* scales;      /* [N, K/group_size] */
+    const void* biases;      /* [N, K/group_size] */
+    const void* bias;        /* [N] or NULL */
+    void* y;                 /* [M, N] row-major, fully overwritten */
+    int64_t N;
+    int bits;
+    int group_size;
+} gbxq_segment;
+int gbxq_qmm_grouped(const gbxq_segment* segs_host, int nseg, const void* x, int64_t M, int64_t K, int dtype,
+                     void* stream);
+
 /* Scratch bytes gbxq_qmm may use for these arguments (0 today for every shipped kernel). */
 size_t gbxq_workspace_bytes(int64_t M, int64_t N, int64_t K, int bits, int group_size, int dtype);
 

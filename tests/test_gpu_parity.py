@@ -433,3 +433,57 @@ def test_cuda_graph_capture(cuda_device):
     torch.cuda.synchronize()
     ref = g.quantized_matmul(x, d["qweight"], d["scales"], d["zeros"], True, 64, 4)
     assert torch.equal(out, ref) and not torch.equal(out, eager)
+
+
+# ---------------------------------------------------------------------------------- grouped launch
+class _Seg:
+    """QuantizedLinear-like holder for quantized_matmul_grouped."""
+
+    def __init__(self, d, bits, gs):
+        self.qweight, self.scales, self.zeros = d["qweight"], d["scales"], d["zeros"]
+        self.bias = d.get("bias")
+        self.bits, self.group_size = bits, gs
+
+
+@pytest.mark.parametrize("M", (1, 2, 4, 7))
+@pytest.mark.parametrize("gs", (64, 128))
+def test_qmm_grouped_matches_single_calls_and_oracle(cuda_device, M, gs):
+    """q|k|v and gate|up as one gbxq_qmm_grouped call (layer-mix: different bits per segment, Qwen2 biases):
+    bitwise equal to one gbxq_qmm call per segment, and within the path's tolerance of the oracle.
+    M = 7 and the 3-bit segment exercise the per-segment fallback inside the same entry point."""
+    g = _ops()
+    from gbx_lm_b200 import ops
+
+    K = 2048
+    for combo in (((4, 512), (4, 128), (4, 128)), ((2, 1024), (4, 1024)), ((8, 96), (2, 300), (4, 1), (4, 149)),
+                  ((4, 256), (3, 128)), ((4, 4096), (2, 4096))):
+        segs, raw = [], []
+        for i, (bits, N) in enumerate(combo):
+            L = A.synth_layer(N, K, bits, gs, seed=7 * i + bits + N, with_bias=(i == 1))
+            raw.append(L)
+            segs.append(_Seg(layer_to_cuda(L, cuda_device), bits, gs))
+        xb = A.synth_x(M, K, seed=5 + M)
+        x = bf16_from_bits(xb, cuda_device)
+        n0 = ops.launch_count()
+        ys = g.quantized_matmul_grouped(x, segs)
+        launches = ops.launch_count() - n0
+        fusable = M <= 4 and all(b in (2, 4, 8) for b, _ in combo)
+        assert launches == (1 if fusable else len(combo)), (combo, M, launches)
+        for sg, L, y, (bits, N) in zip(segs, raw, ys, combo):
+            single = g.quantized_matmul(x, sg.qweight, sg.scales, sg.zeros, True, gs, bits, bias=sg.bias)
+            assert y.shape == (M, N) and torch.equal(y, single), (combo, bits, N)
+            ref = A.quantized_matmul(xb, L["qweight"], L["scales"], L["zeros"], gs, bits, "bf16", "f64", bias=L.get("bias"))
+            assert_close_to_truth(y, ref, f"grouped b{bits} N{N} M{M}")
+
+
+def test_qmm_grouped_validation(cuda_device):
+    g = _ops()
+    K = 256
+    a = _Seg(layer_to_cuda(A.synth_layer(64, K, 4, 64, seed=1), cuda_device), 4, 64)
+    b = _Seg(layer_to_cuda(A.synth_layer(64, 512, 4, 64, seed=2), cuda_device), 4, 64)
+    x = bf16_from_bits(A.synth_x(1, K, seed=3), cuda_device)
+    with pytest.raises(ValueError):
+        g.quantized_matmul_grouped(x, [a, b])  # K mismatch
+    with pytest.raises(ValueError):
+        g.quantized_matmul_grouped(x, [a] * 5)  # too many segments
+    assert g.quantized_matmul_grouped(x, []) == []

@@ -20,9 +20,9 @@ def peak():
     return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
 
 
-def bench_shape(n, k, bits, gs, m, kernel, dev, iters=30, min_bytes=320 << 20):
+def bench_shape(n, k, bits, gs, m, kernel, dev, iters=30, min_bytes=320 << 20, l2=False):
     wbytes = n * k * bits // 8
-    copies = max(2, min(64, (min_bytes + wbytes - 1) // wbytes))
+    copies = 1 if l2 else max(2, min(64, (min_bytes + wbytes - 1) // wbytes))
     gen = torch.Generator(device=dev).manual_seed(0)
     nb = (1 << bits) - 1
     ws, ss, zs = [], [], []
@@ -64,6 +64,7 @@ def main():
     ap.add_argument("--json", default=None)
     ap.add_argument("--ms", default="1")
     ap.add_argument("--shapes", default="8b")
+    ap.add_argument("--l2", action="store_true", help="one weight copy: launches after the first stream from L2 (compute/L2 ceiling, not a roofline number)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     pk = peak()
@@ -80,7 +81,7 @@ def main():
         for (bits, gs) in combos:
             for m in ms:
                 try:
-                    us, gbs = bench_shape(n, k, bits, gs, m, args.kernel, dev)
+                    us, gbs = bench_shape(n, k, bits, gs, m, args.kernel, dev, l2=args.l2)
                 except Exception as e:  # noqa: BLE001
                     print(name, n, k, bits, gs, m, "ERR", e)
                     continue

@@ -47,4 +47,5 @@ t0 = t[0, 0]
 names = ["entry", "waited", "prologue", "stage0", "loopend", "ctabar", "exit"]
 print(f"N={n} K={k} bits={bits} gs={gs} pdl={pdl}: ns relative to launch 0 entry; per launch: " + " ".join(names))
 for i in range(L):
-    print(i, " ".join(f"{int(v - t0):7d}" for v in t[i, :7]), "  | dur", int(t[i, 6] - t[i, 0]), " exit->next waited", int(t[i + 1, 1] - t[i, 6]) if i + 1 < L else "")
+    print(i, " ".join(f"{int(v - t0):7d}" for v in t[i, :7]), "  | dur", int(t[i, 6] - t[i, 0]), " wait->x", int(t[i, 7] - t[i, 1]),
+          " exit->next waited", int(t[i + 1, 1] - t[i, 6]) if i + 1 < L else "")
