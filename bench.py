@@ -182,7 +182,29 @@ def run_gbxq(args):
         else:
             calls.append((layers[i][0], [layers[i][1]])); i += 1
 
+    # --stream 1: the calls of a step as a chain executed by ONE persistent launch (gbxq_qmm_stream), every call
+    # ordered after the one before it (dep = previous: exactly the semantics of the launch-per-call step below).
+    # Under TP the chain is cut at each all-reduce (after o_proj / down_proj).
+    chains = []
+    if args.stream:
+        cur = ops.StreamChain(M)
+        for p, ms in calls:
+            ys = cur.add(xbuf[ms[0].input_dims], ms)
+            if world > 1 and p in ("o_proj", "down_proj"):
+                chains.append((cur.finalize(), ys[0]))
+                cur = ops.StreamChain(M)
+        if len(cur):
+            chains.append((cur.finalize(), None))
+        stream_y = ys[0]
+
     def step():
+        if args.stream:
+            for ch, ar in chains:
+                ch.run()
+                if ar is not None:
+                    dist.all_reduce(ar)
+            outs[0] = stream_y
+            return
         y = None
         for p, ms in calls:
             if len(ms) == 1:
@@ -236,6 +258,8 @@ def run_gbxq(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
+    if args.stream and any(ch.timed_out() for ch, _ in chains):
+        raise SystemExit("gbxq_qmm_stream: a CTA gave up waiting (grid not co-resident); the measurement is void")
 
     # ---- e2e: the same step through the public API with HOST buffers (pinned), copies inside the timed region
     def e2e_step():
@@ -290,12 +314,14 @@ def run_gbxq(args):
             "bytes_per_step": bytes_step, "l2": "inputs larger than L2 (weights per step >> 126 MB)",
             "parallelism": f"tp{world}" if world > 1 else "single", "launch": "cuda_graph",
             "calls_per_step": len(calls), "grouped_qkv_gate_up": bool(args.grouped),
+            "chain_launch": ({"launches_per_step": len(chains), **chains[0][0].info} if args.stream else None),
         },
         "decode_tok_s_qmm_only": round(1e3 / ms_step * M, 2),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "gbxq::gemv_kernel (all launches of the step)",
-                     "bytes_per_launch_avg": rank_bytes // len(plan),
+                     "kernel": ("gbxq::stream_kernel (persistent chain launch: the mmv8 body over every call of the step)"
+                                if args.stream else "gbxq::mmv8_kernel / mmv8_grouped_kernel (all launches of the step)"),
+                     "bytes_per_launch_avg": rank_bytes // max(launches_per_step, 1),
                      "avg_launch_us": round(ms_step * 1e3 / max(launches_per_step, 1), 3)},
         "e2e": {"value": round(bytes_step / (e2e_ms * 1e-3) / 1e9, 2), "unit": UNIT,
                 "h2d_bytes_per_step": int(h_in.numel() * 2), "d2h_bytes_per_step": int(h_out.numel() * 2),
@@ -402,6 +428,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--grouped", type=int, default=1, help="1: q|k|v and gate|up as one gbxq_qmm_grouped call each (as the model does)")
+    ap.add_argument("--stream", type=int, default=0, help="1: the step's calls as one persistent chain launch (gbxq_qmm_stream); 0: one launch per call")
     ap.add_argument("--pdl", type=int, default=2, help="GBXQ_OPT_PDL (0 plain launches, 1 PDL, 2 PDL + early weight streaming)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -21,6 +21,8 @@ EXPORTS = (
     "gbxq_qmm",
     "gbxq_qmm_ex",
     "gbxq_qmm_grouped",
+    "gbxq_stream_plan",
+    "gbxq_qmm_stream",
     "gbxq_workspace_bytes",
     "gbxq_dequantize",
     "gbxq_select_kernel",
@@ -41,6 +43,25 @@ class Segment(ctypes.Structure):
         ("qweight", ctypes.c_void_p), ("scales", ctypes.c_void_p), ("biases", ctypes.c_void_p), ("bias", ctypes.c_void_p),
         ("y", ctypes.c_void_p), ("N", ctypes.c_int64), ("bits", ctypes.c_int), ("group_size", ctypes.c_int),
     ]
+
+
+DEP_PREV, DEP_NONE = -2, -1
+
+
+class StreamCall(ctypes.Structure):
+    """struct gbxq_stream_call (include/gbxq.h)."""
+
+    _fields_ = [("x", ctypes.c_void_p), ("K", ctypes.c_int64), ("nseg", ctypes.c_int), ("dep", ctypes.c_int),
+                ("segs", Segment * MAX_SEGMENTS)]
+
+
+class StreamInfo(ctypes.Structure):
+    """struct gbxq_stream_info (include/gbxq.h)."""
+
+    _fields_ = [("ncalls", ctypes.c_int32), ("grid", ctypes.c_int32), ("smem_bytes", ctypes.c_int32),
+                ("group_size", ctypes.c_int32), ("mt", ctypes.c_int32), ("stages", ctypes.c_int32),
+                ("slot_bytes", ctypes.c_uint32), ("reserved", ctypes.c_uint32), ("blob_bytes", ctypes.c_uint64),
+                ("counter_bytes", ctypes.c_uint64)]
 
 
 class GbxqError(RuntimeError):
@@ -82,6 +103,10 @@ def get() -> ctypes.CDLL:
     lib.gbxq_qmm_ex.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, ci, ci, ci, ci, vp, sz, vp]
     lib.gbxq_qmm_grouped.restype = ci
     lib.gbxq_qmm_grouped.argtypes = [ctypes.POINTER(Segment), ci, vp, i64, i64, ci, vp]
+    lib.gbxq_stream_plan.restype = ci
+    lib.gbxq_stream_plan.argtypes = [ctypes.POINTER(StreamCall), ci, i64, ci, vp, sz, ctypes.POINTER(StreamInfo)]
+    lib.gbxq_qmm_stream.restype = ci
+    lib.gbxq_qmm_stream.argtypes = [ctypes.POINTER(StreamInfo), vp, vp, vp]
     lib.gbxq_workspace_bytes.restype = sz
     lib.gbxq_workspace_bytes.argtypes = [i64, i64, i64, ci, ci, ci]
     lib.gbxq_dequantize.restype = ci

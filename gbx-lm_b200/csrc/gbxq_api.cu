@@ -27,6 +27,7 @@ int device_sm_count() {
 
 // M above which the tensor-core kernel takes over from the streaming GEMV.  The GEMV re-streams
 // the weights once per 2 tokens, the GEMM dequantises each weight once per <=256 tokens.
+static constexpr int64_t kMmvMaxM = 2;
 static constexpr int64_t kSkinnyMaxM = 16;  // 2 passes of 8 tokens; above that the tcgen05 GEMM amortises better
 
 static int select(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype, const void* x, const void* w,
@@ -34,9 +35,11 @@ static int select(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype, 
     const bool skinny_ok = skinny_supported(M, N, K, bits, gs, dtype, x, w, y);
     const bool gemv_ok = gemv_supported(M, N, K, bits, gs, dtype, x, w, y);
     const bool gemm_ok = gemm_supported(M, N, K, bits, gs, dtype, x, w, y);
-    // tensor-pipe matrix-vector kernels: 1..4 tokens; the integer one is the faster (profiles/)
-    if (M <= 4 && mmv8_supported(M, N, K, bits, gs, dtype, x, w, y)) return GBXQ_KERNEL_MMV8;
-    if (M <= 4 && mmv_supported(M, N, K, bits, gs, dtype, x, w, y)) return GBXQ_KERNEL_MMV;
+    // tensor-pipe matrix-vector kernels: their IMMA/HMMA work grows with the token count, so they win at 1-2 tokens
+    // only (profiles/r01g_micro_m234.txt: q/o M=3 9.6 us against 7.1 us for the 8-token skinny kernel; M=2 6.2 vs 7.1)
+    if (M <= kMmvMaxM && mmv8_supported(M, N, K, bits, gs, dtype, x, w, y)) return GBXQ_KERNEL_MMV8;
+    if (M <= kMmvMaxM && mmv_supported(M, N, K, bits, gs, dtype, x, w, y)) return GBXQ_KERNEL_MMV;
+    if (M > kMmvMaxM && M <= 4 && !skinny_ok && mmv8_supported(M, N, K, bits, gs, dtype, x, w, y)) return GBXQ_KERNEL_MMV8;
     // measured on B200 (profiles/): the FMA-pipe GEMV wins at M <= 2, the tensor-pipe skinny kernel costs the
     // same for 1..8 tokens and wins from M = 3
     if (gemv_ok && M <= 2) return GBXQ_KERNEL_GEMV;
@@ -79,6 +82,10 @@ uint64_t gbxq_launch_count(void) { return g_launches.load(std::memory_order_rela
 // to `buf_dev`: entry, after griddepcontrol.wait, after the prologue, first stage landed, main loop done, CTA barrier,
 // exit.  tools/timeline.py prints them.
 void gbxq_debug_timeline(unsigned long long* buf_dev, int launches) { mmv8_debug_timeline(buf_dev, launches); }
+
+void gbxq_debug_stream_timeline(void* host_blob, int ncalls, unsigned long long* dbg_dev) {
+    stream_debug_patch(host_blob, ncalls, dbg_dev);
+}
 
 int gbxq_set_option(int key, int value) {
     if (key == GBXQ_OPT_PDL) {
@@ -162,7 +169,7 @@ int gbxq_qmm_grouped(const gbxq_segment* segs, int nseg, const void* x, int64_t 
         if ((uintptr_t)s.qweight & 3) return GBXQ_EALIGN;
     }
     if (M == 0) return GBXQ_OK;
-    if (dtype == GBXQ_BF16 && nseg >= 2 && nseg <= GBXQ_MAX_SEGMENTS) {
+    if (dtype == GBXQ_BF16 && nseg >= 2 && nseg <= GBXQ_MAX_SEGMENTS && M <= kMmvMaxM) {
         const int rc = launch_mmv8_grouped(segs, nseg, x, M, K, (cudaStream_t)stream);
         if (rc != GBXQ_EUNSUPPORTED) return rc;
     }
@@ -173,6 +180,15 @@ int gbxq_qmm_grouped(const gbxq_segment* segs, int nseg, const void* x, int64_t 
         if (rc != GBXQ_OK) return rc;
     }
     return GBXQ_OK;
+}
+
+int gbxq_stream_plan(const gbxq_stream_call* calls_host, int ncalls, int64_t M, int dtype, void* host_blob,
+                     size_t blob_capacity, gbxq_stream_info* info) {
+    return stream_plan(calls_host, ncalls, M, dtype, host_blob, blob_capacity, info);
+}
+
+int gbxq_qmm_stream(const gbxq_stream_info* info, const void* blob_dev, void* counters_dev, void* stream) {
+    return launch_stream(info, blob_dev, counters_dev, (cudaStream_t)stream);
 }
 
 int gbxq_dequantize(const uint32_t* qweight, const void* scales, const void* biases, void* w_out, int64_t N,

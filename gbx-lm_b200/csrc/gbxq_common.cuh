@@ -169,6 +169,10 @@ int launch_mmv8(const void* x, const uint32_t* w, const void* s, const void* b, 
                 int64_t N, int64_t K, int bits, int gs, cudaStream_t st);
 void mmv8_debug_timeline(unsigned long long* buf, int launches);
 int launch_mmv8_grouped(const gbxq_segment* segs, int nseg, const void* x, int64_t M, int64_t K, cudaStream_t st);
+int stream_plan(const gbxq_stream_call* calls, int ncalls, int64_t M, int dtype, void* host_blob, size_t cap,
+                gbxq_stream_info* info);
+void stream_debug_patch(void* host_blob, int ncalls, unsigned long long* dbg_dev);
+int launch_stream(const gbxq_stream_info* info, const void* blob, void* counters, cudaStream_t st);
 void mmv_set_pdl_mode(int mode);
 int mmv_get_pdl_mode();
 bool gemm_supported(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype, const void* x, const void* w,

@@ -9,7 +9,8 @@ namespace mmv8 {
 
 constexpr int kCW = 8;                        // consumer warps
 constexpr int kThreads = (kCW + 1) * 32;      // + producer warp
-constexpr int kMaxStages = 4;
+constexpr int kMaxStages = 8;                // barrier slots; one-call launches plan at most kPlanStages
+constexpr int kPlanStages = 4;
 #ifndef GBXQ_MMV8_MINCTAS
 #define GBXQ_MMV8_MINCTAS 2
 #endif
@@ -106,9 +107,31 @@ struct Mmv8Params {
     int spr0, spr1;           // rows per stage for CTAs with rows_base / rows_base+1 rows (balanced, whole MMA sets)
 };
 
-// BITS, GS = group size, MT = tokens (1, 2, 4), CPW = chunk columns per warp, R = rows per warp and stage (4 or 8)
-template <int BITS, int GS, int MT, int CPW, int R>
-__device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, uint8_t* smem) {
+// State a persistent chain launch (gbxq_stream.cu) carries from one call to the next: the ring position and the
+// device-wide completion counters that order the calls (x of a call may be the y of any earlier one).
+struct StreamCtx {
+    int s;                      // ring slot of the next stage
+    uint32_t phase;             // its parity
+    const unsigned* wait_cnt;   // counter that must reach wait_target before x is read / y is written (nullptr: none)
+    unsigned wait_target;
+    unsigned* done_cnt;         // incremented once by this CTA when its part of y is in global memory
+    unsigned* err;              // set to 1 when a wait timed out (the launch then runs to its end unordered)
+    bool dead;                  // thread 0: a wait has timed out, stop waiting
+};
+
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kCW * 32) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// BITS, GS = group size, MT = tokens (1, 2, 4), CPW = chunk columns per warp, R = rows per warp and stage (4 or 8).
+// STREAM = false: the whole CTA of a one-call launch (barrier set-up, producer warp, consumers, epilogue).
+// STREAM = true: one call of a persistent chain, entered by the kCW consumer warps only; barriers (empty barriers
+// initialised to kCW arrivals) and the producer live in the caller, `sc` carries the ring position.
+template <int BITS, int GS, int MT, int CPW, int R, bool STREAM = false>
+__device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, uint8_t* smem, StreamCtx* sc = nullptr) {
     constexpr int CQ = GS / 4;
     using GE = Geo<BITS, CQ>;
     constexpr int NWORD = GE::NWORD, NCLASS = GE::NCLASS, NMMA = GE::NMMA;
@@ -137,24 +160,45 @@ __device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, ui
     const int active_warps = p.cw * p.rg;
     const int slots = 2 * p.cw;
 
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < nstg; s++) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], active_warps);
+    if constexpr (!STREAM) {
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < nstg; s++) {
+                mbar_init(&full_bar[s], 1);
+                mbar_init(&empty_bar[s], active_warps);
+            }
+            fence_mbar_init();
         }
-        fence_mbar_init();
+        __syncthreads();
+        if (threadIdx.x == 0) griddep_launch();  // the next kernel of the stream may become resident now
+    } else {
+        // every earlier call this one depends on must be complete on ALL CTAs before x is read or y overwritten
+        if (threadIdx.x == 0 && sc->wait_cnt != nullptr && !sc->dead) {
+            const unsigned long long t0 = gtime();
+            while (ld_acquire_gpu(sc->wait_cnt) < sc->wait_target) {
+                if (gtime() - t0 > 2000000000ull) {  // 2 s: a CTA of the grid is not resident; never hang the device
+                    atomicExch(sc->err, 1u);
+                    sc->dead = true;
+                    break;
+                }
+            }
+            __threadfence();
+        }
+        consumer_bar();
+        STAMP(5);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) griddep_launch();  // the next kernel of the stream may become resident now
+    int s = 0;
+    uint32_t phase = 0;
+    if constexpr (STREAM) {
+        s = sc->s;
+        phase = sc->phase;
+    }
 
-    if (warp == kCW) {
+    if (!STREAM && warp == kCW) {
         // ===================== producer warp: one elected lane drives the TMA engine =====================
         if (lane == 0 && rows > 0) {
             if (!p.early_weights) griddep_wait();
             const uint8_t* wsrc = p.w + (uint64_t)r0 * p.row_bytes;
             const uint32_t g2 = (uint32_t)p.G * 2u;
-            int s = 0;
-            uint32_t phase = 0;
             for (int ra = 0; ra < rows; ra += spr) {
                 mbar_wait(&empty_bar[s], phase ^ 1u);
                 int nr = rows - ra;
@@ -188,25 +232,40 @@ __device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, ui
         // for part B iff t == sB; this lane's meaningful part (if any) multiplies group slice t
         const bool mean = (t & 1) == (g & 1);
 
-        griddep_wait();  // x (and y) belong to the previous kernels of the stream
+        if constexpr (!STREAM) griddep_wait();  // x (and y) belong to the previous kernels of the stream
         STAMP(1);
 
         // ---- stationary operands: digit fragments of the activations, per-group power-of-two factors, group sums
         uint32_t bfr[MT][CPW][NCLASS][NMMA][2];
         float pw[MT][CPW];  // 2^(e-13) / CMUL of group slice t of chunk column j (the slice this lane's accumulators need)
         float* myx = xsc + warp * (CPW * S * MT);
+        // activations of up to JB chunk columns are requested together: one L2 round trip per batch instead of one per
+        // column (K = 14336 has 8 columns per warp; fetched one by one the prologue was 4 us, profiles/r01h_*)
+        constexpr int JBmax = 64 / CQ;  // at most 8 uint4 (32 registers) in flight per lane
+        constexpr int JB = CPW < JBmax ? CPW : JBmax;
 #pragma unroll
         for (int m = 0; m < MT; m++) {
 #pragma unroll
-            for (int j = 0; j < CPW; j++) {
-                const int c = cwi + j * p.cw;
+            for (int j0 = 0; j0 < CPW; j0 += JB) {
+            uint4 raw[JB][CQ / 8];
+#pragma unroll
+            for (int jj = 0; jj < JB; jj++) {
+                const int c = cwi + (j0 + jj) * p.cw;
                 const bool ld = (c < p.nch) && (m < p.M);
                 const int64_t k0 = ((int64_t)c * S + bsl) * GS + t * CQ;
-                uint32_t n32[CQ / 2];  // n32[i] = codes (2i, 2i+1) of the chunk, natural order
                 const uint4* src = reinterpret_cast<const uint4*>(p.x + (size_t)m * p.K + k0);
 #pragma unroll
+                for (int v = 0; v < CQ / 8; v++)
+                    // chain launches read activations another SM wrote during this launch: L2-coherent loads there
+                    raw[jj][v] = ld ? (STREAM ? __ldcg(src + v) : __ldg(src + v)) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int jj = 0; jj < JB; jj++) {
+                const int j = j0 + jj;
+                uint32_t n32[CQ / 2];  // n32[i] = codes (2i, 2i+1) of the chunk, natural order
+#pragma unroll
                 for (int v = 0; v < CQ / 8; v++) {
-                    const uint4 q = ld ? __ldg(src + v) : make_uint4(0u, 0u, 0u, 0u);
+                    const uint4 q = raw[jj][v];
                     n32[4 * v + 0] = q.x; n32[4 * v + 1] = q.y; n32[4 * v + 2] = q.z; n32[4 * v + 3] = q.w;
                 }
                 // |x| maximum of the chunk as packed 16-bit lanes; sum of x in fp32
@@ -266,6 +325,7 @@ __device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, ui
                             bfr[m][j][c2][u][h] = r;
                         }
             }
+            }
         }
         __syncwarp();
         const int brow = lane / LPR, bq = lane % LPR;
@@ -294,8 +354,6 @@ __device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, ui
         const uint32_t sstride = (uint32_t)p.cw * S * 2u;
 
         STAMP(2);
-        int s = 0;
-        uint32_t phase = 0;
         for (int ra = 0; ra < rows; ra += spr) {
             int nr = rows - ra;
             if (nr > spr) nr = spr;
@@ -399,12 +457,30 @@ __device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, ui
             }
         }
     }
+    else if (STREAM && rows > 0) {
+        // idle warps of a narrow call keep the ring's arrival counts whole
+        for (int ra = 0; ra < rows; ra += spr) {
+            mbar_wait(&full_bar[s], phase);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+            if (++s == nstg) {
+                s = 0;
+                phase ^= 1u;
+            }
+        }
+    }
     STAMP(4);
-    __syncthreads();
-    STAMP(5);
-    griddep_wait();  // every thread stores y below (returns at once when a consumer warp has already waited)
+    if constexpr (STREAM) {
+        consumer_bar();
+        sc->s = s;
+        sc->phase = phase;
+    } else {
+        __syncthreads();
+        STAMP(5);
+        griddep_wait();  // every thread stores y below (returns at once when a consumer warp has already waited)
+    }
     // ---- epilogue: one rounding to bf16, optional bias as a second rounded add, coalesced store
-    for (int i = threadIdx.x; i < rows * MT; i += kThreads) {
+    for (int i = threadIdx.x; i < rows * MT; i += (STREAM ? kCW * 32 : kThreads)) {
         const int m = i / rows, r = i - m * rows;
         if (m < p.M) {
             float tot = 0.f;
@@ -415,6 +491,13 @@ __device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, ui
         }
     }
     STAMP(6);
+    if constexpr (STREAM) {
+        consumer_bar();  // all of this CTA's y stores are issued (and ysum / the call descriptor may be reused)
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(sc->done_cnt, 1u);
+        }
+    }
 }
 
 
@@ -462,7 +545,7 @@ inline Plan make_plan(int64_t M, int64_t N, int64_t K, int bits, int gs, int gri
     const uint32_t wpart = (uint32_t)(((int64_t)pl.tr * row_bytes + 127) & ~(int64_t)127);
     pl.sb_off = wpart;
     pl.slot_bytes = wpart + (uint32_t)((2 * (int64_t)pl.tr * G * 2 + 127) & ~(int64_t)127);
-    pl.stages = kMaxStages;
+    pl.stages = kPlanStages;
     while (pl.stages > 2 && (size_t)pl.stages * pl.slot_bytes > (size_t)ring_kb * 1024) pl.stages--;
     int grid = grid_want > 0 ? grid_want : device_sm_count() * grid_mult;
     const int64_t min_rows = pl.tr;
@@ -475,6 +558,14 @@ inline Plan make_plan(int64_t M, int64_t N, int64_t K, int bits, int gs, int gri
     if (pl.smem > 110 * 1024) return pl;
     pl.ok = true;
     return pl;
+}
+
+// Relative cost of a segment when CTAs are shared out between the segments of one call.  Measured steady state
+// (profiles/r01b_big.txt): 4-bit rows stream at 0.90 of HBM, 2-bit rows at 0.50 -- both 10.5e12 codes/s, the kernel's
+// unpack/IMMA ceiling -- so a row costs max(its bytes, K codes at that ceiling = 0.5625 byte-equivalents per code).
+inline double segment_cost(int64_t N, int64_t K, int bits, int gs) {
+    const double bytes_per_code = bits / 8.0 + 4.0 / gs;
+    return (double)N * (double)K * (bytes_per_code > 0.5625 ? bytes_per_code : 0.5625);
 }
 
 inline int mmv8_total_ctas() {

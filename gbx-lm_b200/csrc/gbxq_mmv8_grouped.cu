@@ -111,7 +111,7 @@ int launch_mmv8_grouped(const gbxq_segment* segs, int nseg, const void* x, int64
         if (sg.group_size != gs || !(sg.bits == 2 || sg.bits == 4 || sg.bits == 8) || sg.N < 1) return GBXQ_EUNSUPPORTED;
         if (((uintptr_t)sg.qweight | (uintptr_t)sg.scales | (uintptr_t)sg.biases) & 15) return GBXQ_EUNSUPPORTED;
         if ((uintptr_t)sg.y & 1) return GBXQ_EUNSUPPORTED;
-        bytes[i] = (double)sg.N * (double)(K * sg.bits / 8 + 4 * (K / gs));
+        bytes[i] = segment_cost(sg.N, K, sg.bits, gs);
         total += bytes[i];
     }
     // CTAs per segment in proportion to its bytes (largest-remainder rounding, at least one each)

@@ -225,7 +225,7 @@ def quantized_matmul_grouped(x: torch.Tensor, layers: Sequence) -> List[torch.Te
     """The projections that read the same activations -- q_proj|k_proj|v_proj (gbx_lm/models/qllama.py:76) and
     gate_proj|up_proj (qllama.py:115) -- as ONE call: `layers` are QuantizedLinear-like objects (attributes
     qweight/scales/zeros/bias/group_size/bits).  Results are identical to calling each layer on x; at decode
-    batch sizes (M <= 4) with a common group size the work is a single kernel launch (gbxq_qmm_grouped)."""
+    batch sizes (M <= 2) with a common group size the work is a single kernel launch (gbxq_qmm_grouped)."""
     layers = list(layers)
     if len(layers) > _lib.MAX_SEGMENTS:
         raise ValueError(f"[quantized_matmul_grouped] at most {_lib.MAX_SEGMENTS} projections per call")
@@ -233,6 +233,118 @@ def quantized_matmul_grouped(x: torch.Tensor, layers: Sequence) -> List[torch.Te
         x, [l.qweight for l in layers], [l.scales for l in layers], [l.zeros for l in layers],
         [getattr(l, "bias", None) for l in layers], [int(l.group_size) for l in layers], [int(l.bits) for l in layers],
     )
+
+
+class StreamChain:
+    """An ordered chain of decode-sized QuantizedLinear forwards executed by ONE persistent kernel launch
+    (gbxq_stream_plan / gbxq_qmm_stream, include/gbxq.h): the q|k|v, o_proj, gate|up, down_proj calls of the blocks
+    (gbx_lm/models/qllama.py:76-115) in issue order.  Semantics and results are those of issuing the calls one after
+    another (bitwise equal to `quantized_matmul` / `quantized_matmul_grouped`); later calls' weights stream into
+    shared memory while earlier calls finish.
+
+        chain = StreamChain(M)
+        ys = chain.add(x_buf, [q, k, v])          # x_buf: persistent [M, K] bf16 buffer; returns the output buffers
+        (o,) = chain.add(attn_buf, [o_proj])      # dep="prev" (stream order) by default, dep=None: x is external
+        chain.finalize()
+        chain.run()                               # enqueue on the current stream (CUDA-graph capturable)
+
+    Buffers are fixed at plan time (as in a CUDA graph): write new activations INTO x_buf, read results from ys."""
+
+    def __init__(self, m: int):
+        self.m = int(m)
+        self._calls = []
+        self._keep = []
+        self._info = None
+        self._blob = None
+        self._counters = None
+        self.device = None
+
+    def add(self, x: torch.Tensor, layers: Sequence, dep="prev", out: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
+        if self._info is not None:
+            raise RuntimeError("StreamChain is finalized")
+        layers = list(layers)
+        if not 1 <= len(layers) <= _lib.MAX_SEGMENTS:
+            raise ValueError(f"[StreamChain] 1..{_lib.MAX_SEGMENTS} projections per call")
+        dev = _require_cuda(x, *[l.qweight for l in layers])
+        if self.device is None:
+            self.device = dev
+        elif dev != self.device:
+            raise RuntimeError("all tensors of a chain must live on the same CUDA device")
+        if x.dim() != 2 or x.shape[0] != self.m or not x.is_contiguous() or x.dtype != torch.bfloat16:
+            raise ValueError("[StreamChain] x must be a contiguous [M, K] bf16 buffer")
+        k = x.shape[1]
+        call = _lib.StreamCall()
+        call.x, call.K, call.nseg = x.data_ptr(), k, len(layers)
+        if dep == "prev":
+            call.dep = _lib.DEP_PREV
+        elif dep is None:
+            call.dep = _lib.DEP_NONE
+        else:
+            call.dep = int(dep)
+        outs = []
+        for i, l in enumerate(layers):
+            _as_u32_ptr_tensor(l.qweight)
+            n, _ = _check_shapes(l.qweight, l.scales, l.zeros, int(l.group_size), int(l.bits), k)
+            if l.scales.dtype != torch.bfloat16:
+                raise ValueError("[StreamChain] scales/biases must be bf16")
+            w, sc, b = l.qweight.contiguous(), l.scales.contiguous(), l.zeros.contiguous()
+            bi = getattr(l, "bias", None)
+            if bi is not None:
+                if bi.dtype != x.dtype or bi.numel() != n:
+                    raise ValueError("[StreamChain] bias must be [N] in the activation dtype")
+                bi = bi.contiguous()
+            y = out[i] if out is not None else torch.empty((self.m, n), dtype=x.dtype, device=x.device)
+            if y.shape != (self.m, n) or y.dtype != x.dtype or not y.is_contiguous():
+                raise ValueError("[StreamChain] out buffers must be contiguous [M, N] in the activation dtype")
+            self._keep.append((x, w, sc, b, bi, y))
+            outs.append(y)
+            call.segs[i] = _lib.Segment(w.data_ptr(), sc.data_ptr(), b.data_ptr(), bi.data_ptr() if bi is not None else None,
+                                        y.data_ptr(), n, int(l.bits), int(l.group_size))
+        self._calls.append(call)
+        return outs
+
+    def __len__(self) -> int:
+        return len(self._calls)
+
+    def finalize(self, debug_timeline: bool = False) -> "StreamChain":
+        import ctypes
+
+        lib = _lib.get()
+        n = len(self._calls)
+        arr = (_lib.StreamCall * max(n, 1))(*self._calls)
+        info = _lib.StreamInfo()
+        _lib.check(lib.gbxq_stream_plan(arr, n, self.m, _lib.BF16, None, 0, ctypes.byref(info)), "gbxq_stream_plan")
+        host = torch.empty(int(info.blob_bytes), dtype=torch.uint8)
+        _lib.check(lib.gbxq_stream_plan(arr, n, self.m, _lib.BF16, host.data_ptr(), host.numel(), ctypes.byref(info)),
+                   "gbxq_stream_plan")
+        if debug_timeline:  # development aid: 8 globaltimer stamps per call from CTA 0 (tools/stream_timeline.py)
+            self.timeline = torch.zeros((n, 8), dtype=torch.int64, device=self.device)
+            lib.gbxq_debug_stream_timeline.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+            lib.gbxq_debug_stream_timeline.restype = None
+            lib.gbxq_debug_stream_timeline(host.data_ptr(), n, self.timeline.data_ptr())
+        self._blob = host.to(self.device)
+        self._counters = torch.zeros(int(info.counter_bytes) // 4, dtype=torch.int32, device=self.device)
+        self._info = info
+        return self
+
+    @property
+    def info(self) -> dict:
+        i = self._info
+        return {f: getattr(i, f) for f, _ in _lib.StreamInfo._fields_}
+
+    def run(self) -> None:
+        import ctypes
+
+        if self._info is None:
+            self.finalize()
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream().cuda_stream
+            rc = _lib.get().gbxq_qmm_stream(ctypes.byref(self._info), self._blob.data_ptr(), self._counters.data_ptr(), st)
+        _lib.check(rc, "gbxq_qmm_stream")
+
+    def timed_out(self) -> bool:
+        """True if a launch ever gave up waiting for a CTA (synchronises; for tests and health checks)."""
+        return bool(self._counters[-1].item())
 
 
 def dequantize(w: torch.Tensor, scales: torch.Tensor, biases: torch.Tensor, group_size: int = 64, bits: int = 4) -> torch.Tensor:

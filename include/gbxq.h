@@ -117,7 +117,7 @@ int gbxq_qmm_ex(const void* x, const uint32_t* qweight, const void* scales, cons
  * gate_proj/up_proj calls of the reference (gbx_lm/models/qllama.py:76,115; gbx_lm/models/qqwen2.py:66,94), whose
  * bit widths differ per projection in layer-mix checkpoints (quantized_linear_gba.py:258-272).
  * Semantics are exactly those of nseg gbxq_qmm calls (y_s[M,N_s] = x . dequant(W_s)^T (+ bias_s)), results are
- * identical to them; when M <= 4 and the segments share K and group_size the work is ONE kernel launch, otherwise
+ * identical to them; when M <= 2 and the segments share K and group_size the work is ONE kernel launch, otherwise
  * the call enqueues one launch per segment.  `segs` is a HOST array read before the call returns.
  */
 #define GBXQ_MAX_SEGMENTS 4
@@ -133,6 +133,48 @@ typedef struct gbxq_segment {
 } gbxq_segment;
 int gbxq_qmm_grouped(const gbxq_segment* segs_host, int nseg, const void* x, int64_t M, int64_t K, int dtype,
                      void* stream);
+
+/*
+ * Chain launch: an ordered list of decode-sized (M <= 4, bf16) quantized matmuls -- the QuantizedLinear forwards of
+ * one decode step in the order the reference's blocks issue them (gbx_lm/models/qllama.py:76-115: q|k|v, o_proj,
+ * gate|up, down_proj per block) -- executed by ONE persistent kernel launch.  Semantics are those of issuing the
+ * calls one after another on a stream: call i reads its x and writes its y only after every call <= dep_i is
+ * complete (dep_i = i-1 by default: plain stream order), and results are bitwise identical to gbxq_qmm /
+ * gbxq_qmm_grouped on the same arguments.  What changes is that the packed weights, scales and biases of LATER calls
+ * keep streaming into the shared-memory rings while earlier calls finish, so HBM does not idle at call borders
+ * (QuantizedLinear parameters are frozen: quantized_linear_gba.py:57-58,162-166).
+ *
+ * Two steps, because weights and activation buffers of a decode loop are fixed: gbxq_stream_plan (host only) checks
+ * the chain and writes a descriptor blob into HOST memory; the caller copies the blob to the device once and then
+ * calls gbxq_qmm_stream any number of times (CUDA-graph capturable, no allocation, no synchronisation).
+ *   dep : index of the last earlier call whose output this call's x may alias; GBXQ_DEP_PREV = the call before it
+ *         (stream order), GBXQ_DEP_NONE = x is not produced inside the chain.
+ *   counters_dev : (ncalls + 2) uint32, zeroed ONCE by the caller before the first launch; the kernel leaves them
+ *         zero again.  Entry ncalls+1 is set to 1 if a CTA ever gave up waiting (grid not co-resident): results
+ *         of that launch are then undefined; the kernel never hangs.
+ * gbxq_stream_plan returns GBXQ_EUNSUPPORTED when a call cannot be served by the chain kernel (M > 4, 3-/6-bit,
+ * fp16/fp32, mixed group sizes): issue such steps as individual gbxq_qmm calls.
+ */
+#define GBXQ_DEP_PREV (-2)
+#define GBXQ_DEP_NONE (-1)
+typedef struct gbxq_stream_call {
+    const void* x;       /* [M, K] */
+    int64_t K;
+    int nseg;            /* 1 .. GBXQ_MAX_SEGMENTS projections reading this x */
+    int dep;
+    gbxq_segment segs[GBXQ_MAX_SEGMENTS];
+} gbxq_stream_call;
+typedef struct gbxq_stream_info {
+    int32_t ncalls, grid, smem_bytes, group_size, mt, stages;
+    uint32_t slot_bytes;
+    uint32_t reserved;
+    uint64_t blob_bytes;     /* size of the descriptor blob */
+    uint64_t counter_bytes;  /* size of the counter array */
+} gbxq_stream_info;
+/* host_blob == NULL: only fills `info` (sizes).  Otherwise writes info->blob_bytes bytes (blob_capacity checked). */
+int gbxq_stream_plan(const gbxq_stream_call* calls_host, int ncalls, int64_t M, int dtype, void* host_blob,
+                     size_t blob_capacity, gbxq_stream_info* info);
+int gbxq_qmm_stream(const gbxq_stream_info* info, const void* blob_dev, void* counters_dev, void* stream);
 
 /* Scratch bytes gbxq_qmm may use for these arguments (0 today for every shipped kernel). */
 size_t gbxq_workspace_bytes(int64_t M, int64_t N, int64_t K, int bits, int group_size, int dtype);

@@ -55,6 +55,45 @@ def test_argument_validation_without_gpu():
     assert lib.gbxq_allreduce_oneshot(p, p, 64, 0, p, p, 256, 2, 2, 1, None) == -3  # rank out of range
 
 
+def test_stream_plan_is_host_only_and_validates():
+    """gbxq_stream_plan never touches the device: sizes, ring geometry and refusals can be checked without a GPU."""
+    from gbx_lm_b200 import _lib
+
+    lib = _lib.get()
+    p = 4096  # fake, 16-byte aligned device addresses; the planner never dereferences them
+
+    def call(K, segs, dep=_lib.DEP_PREV):
+        c = _lib.StreamCall()
+        c.x, c.K, c.nseg, c.dep = p, K, len(segs), dep
+        for i, (bits, N, gs) in enumerate(segs):
+            c.segs[i] = _lib.Segment(p, p, p, None, p, N, bits, gs)
+        return c
+
+    def plan(calls, M=1, dt=0):
+        arr = (_lib.StreamCall * len(calls))(*calls)
+        info = _lib.StreamInfo()
+        rc = lib.gbxq_stream_plan(arr, len(calls), M, dt, None, 0, ctypes.byref(info))
+        return rc, info, arr
+
+    block = [call(4096, [(4, 4096, 64), (2, 1024, 64), (4, 1024, 64)]), call(4096, [(4, 4096, 64)]),
+             call(4096, [(4, 14336, 64), (4, 14336, 64)]), call(14336, [(4, 4096, 64)])]
+    rc, info, arr = plan(block * 4)
+    assert rc == 0 and info.ncalls == 16 and info.grid % 2 == 0 and info.group_size == 64 and info.mt == 1
+    assert 2 <= info.stages <= 8 and info.smem_bytes <= 112 * 1024 and info.stages * info.slot_bytes < info.smem_bytes
+    assert info.counter_bytes == (16 + 2) * 4 and info.blob_bytes > 0
+    buf = ctypes.create_string_buffer(int(info.blob_bytes))
+    assert lib.gbxq_stream_plan(arr, 16, 1, 0, buf, info.blob_bytes - 1, ctypes.byref(info)) == -8  # blob too small
+    assert lib.gbxq_stream_plan(arr, 16, 1, 0, buf, info.blob_bytes, ctypes.byref(info)) == 0
+    assert any(buf.raw)
+    assert plan([call(4096, [(3, 64, 64)])])[0] == -9          # 3-bit: not served by the chain kernel
+    assert plan([call(4096, [(4, 64, 64)])], M=5)[0] == -9      # prefill-sized M
+    assert plan([call(4096, [(4, 64, 64)])], dt=1)[0] == -9     # fp16
+    assert plan([call(4096, [(4, 64, 64)]), call(4096, [(4, 64, 128)])])[0] == -9  # mixed group sizes
+    assert plan([call(4096, [(5, 64, 64)])])[0] == -1
+    assert plan([call(4096, [(4, 64, 64)], dep=3)])[0] == -3    # dependency on a later call
+    assert lib.gbxq_qmm_stream(None, None, None, None) == -6
+
+
 def test_ops_refuse_cpu_tensors():
     import gbx_lm_b200 as g
 

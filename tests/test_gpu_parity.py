@@ -467,8 +467,9 @@ def test_qmm_grouped_matches_single_calls_and_oracle(cuda_device, M, gs):
         n0 = ops.launch_count()
         ys = g.quantized_matmul_grouped(x, segs)
         launches = ops.launch_count() - n0
-        fusable = M <= 4 and all(b in (2, 4, 8) for b, _ in combo)
-        assert launches == (1 if fusable else len(combo)), (combo, M, launches)
+        fusable = M <= 2 and all(b in (2, 4, 8) for b, _ in combo)  # M >= 3 goes to the 8-token skinny kernel per segment
+        # the per-segment fallback may tile M inside a segment (3-/6-bit GEMV: M tiles of 1/2), so only a lower bound there
+        assert (launches == 1) if fusable else (launches >= len(combo)), (combo, M, launches)
         for sg, L, y, (bits, N) in zip(segs, raw, ys, combo):
             single = g.quantized_matmul(x, sg.qweight, sg.scales, sg.zeros, True, gs, bits, bias=sg.bias)
             assert y.shape == (M, N) and torch.equal(y, single), (combo, bits, N)
@@ -487,3 +488,122 @@ def test_qmm_grouped_validation(cuda_device):
     with pytest.raises(ValueError):
         g.quantized_matmul_grouped(x, [a] * 5)  # too many segments
     assert g.quantized_matmul_grouped(x, []) == []
+
+
+# ---------------------------------------------------------------------------------- chain launch (persistent kernel)
+def _chain_layers(cuda_device, gs, spec):
+    """spec: list of calls, each a list of (bits, N) segments; K of call i+1 = N of segment 0 of call i."""
+    calls = []
+    K = spec[0][0]
+    for ci, segs in enumerate(spec[1:]):
+        layers = []
+        for si, (bits, N) in enumerate(segs):
+            L = A.synth_layer(N, K, bits, gs, seed=100 * ci + 7 * si + bits, with_bias=(si == 1))
+            layers.append(_Seg(layer_to_cuda(L, cuda_device), bits, gs))
+        calls.append((K, layers))
+        K = segs[0][1]
+    return calls
+
+
+@pytest.mark.parametrize("M", (1, 2, 4))
+@pytest.mark.parametrize("gs", (64, 128))
+def test_stream_chain_matches_stream_ordered_calls(cuda_device, M, gs):
+    """gbxq_qmm_stream: a chain whose every call reads the y of the call before it (a true dependency, as o_proj on
+    q|k|v and down_proj on gate|up) must be bitwise equal to issuing the calls one by one, launch after launch
+    (counters reset in-kernel), eagerly and replayed from a CUDA graph."""
+    g = _ops()
+    from gbx_lm_b200 import ops
+
+    K0 = 2048
+    kbig = {1: 14336, 2: 8192, 4: 4096}[M]  # widest K the decode kernel takes at this M (stationary-fragment budget)
+    spec = [(K0,), [(4, 4096), (2, 512), (8, 256)], [(4, 2048)], [(2, kbig), (4, kbig)], [(4, 1024), (4, 300)],
+            [(8, 2048)], [(4, 1024), (4, 128), (4, 128)], [(2, 2048)]]
+    calls = _chain_layers(cuda_device, gs, spec)
+    x0 = bf16_from_bits(A.synth_x(M, K0, seed=40 + M), cuda_device)
+
+    def sequential(x):
+        outs = []
+        for K, layers in calls:
+            assert x.shape[1] == K
+            if len(layers) == 1:
+                l = layers[0]
+                ys = [g.quantized_matmul(x, l.qweight, l.scales, l.zeros, True, gs, l.bits, bias=l.bias)]
+            else:
+                ys = g.quantized_matmul_grouped(x, layers)
+            outs.append(ys)
+            x = ys[0]
+        return outs
+
+    want = sequential(x0)
+    chain = ops.StreamChain(M)
+    xin = x0.clone()
+    x, got = xin, []
+    for K, layers in calls:
+        ys = chain.add(x, layers)
+        got.append(ys)
+        x = ys[0]
+    chain.finalize()
+    n0 = ops.launch_count()
+    chain.run()
+    assert ops.launch_count() - n0 == 1
+    torch.cuda.synchronize()
+    assert not chain.timed_out()
+
+    def check(tag):
+        for ci, (w, h) in enumerate(zip(want, got)):
+            for si, (a, b) in enumerate(zip(w, h)):
+                assert torch.isfinite(b.float()).all(), (tag, ci, si)
+                assert torch.equal(a, b), (tag, ci, si, (a.float() - b.float()).abs().max().item())
+
+    check("eager")
+    assert int(chain._counters.abs().sum().item()) == 0  # the kernel leaves its counters at zero
+    for ys in got:
+        for y in ys:
+            y.zero_()
+    for _ in range(3):
+        chain.run()
+    torch.cuda.synchronize()
+    check("repeat")
+    # new activations through a CUDA graph replay
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        chain.run()
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        chain.run()
+    x1 = bf16_from_bits(A.synth_x(M, K0, seed=77 + M), cuda_device)
+    want = sequential(x1)
+    xin.copy_(x1)
+    graph.replay()
+    graph.replay()
+    torch.cuda.synchronize()
+    check("graph")
+    assert not chain.timed_out()
+
+
+def test_stream_chain_against_oracle_and_validation(cuda_device):
+    """First call of a chain against the fp64 truth of the oracle; unsupported chains are refused, not mis-run."""
+    g = _ops()
+    from gbx_lm_b200 import ops
+
+    K, gs = 4096, 64
+    raw = [A.synth_layer(N, K, bits, gs, seed=N + bits) for bits, N in ((4, 1024), (2, 768))]
+    segs = [_Seg(layer_to_cuda(L, cuda_device), b, gs) for L, b in zip(raw, (4, 2))]
+    xb = A.synth_x(1, K, seed=9)
+    x = bf16_from_bits(xb, cuda_device)
+    chain = ops.StreamChain(1)
+    ys = chain.add(x, segs, dep=None)
+    (y2,) = chain.add(x, [segs[0]], dep=None)
+    chain.run()
+    torch.cuda.synchronize()
+    for L, y, b in zip(raw, ys, (4, 2)):
+        ref = A.quantized_matmul(xb, L["qweight"], L["scales"], L["zeros"], gs, b, "bf16", "f64")
+        assert_close_to_truth(y, ref, f"chain b{b}")
+    assert torch.equal(y2, ys[0])
+    bad = ops.StreamChain(1)
+    L3 = A.synth_layer(64, K, 3, gs, seed=1)
+    bad.add(x, [_Seg(layer_to_cuda(L3, cuda_device), 3, gs)])
+    with pytest.raises(RuntimeError):
+        bad.finalize()  # 3-bit rows are not served by the chain kernel: GBXQ_EUNSUPPORTED
