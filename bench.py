@@ -139,6 +139,22 @@ def run_gbxq(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    # row-parallel epilogue: one-shot NVLink all-reduce over peer memory (gbxq_allreduce_oneshot; 8 KB .. 1 MB decode
+    # messages are latency-bound) unless --allreduce nccl, or symmetric memory cannot be set up on this box
+    allreduce, ar_kind = None, "none"
+    if world > 1:
+        ar_kind = "nccl"
+        if args.allreduce == "oneshot":
+            try:
+                from gbx_lm_b200.tp import OneShotAllReduce
+
+                allreduce = OneShotAllReduce(None, dev, capacity_elems=max(1 << 16, 4 * args.batch * 8192))
+                ar_kind = "gbxq_allreduce_oneshot (peer memory over NVLink)"
+            except Exception as e:  # noqa: BLE001
+                ar_kind = f"nccl (one-shot unavailable: {type(e).__name__}: {str(e)[:80]})"
+        if allreduce is None:
+            allreduce = lambda t: dist.all_reduce(t)  # noqa: E731
+
     ops.set_pdl_mode(args.pdl)
     dims, plan = build_plan(args)
     full_plan = plan
@@ -202,7 +218,7 @@ def run_gbxq(args):
             for ch, ar in chains:
                 ch.run()
                 if ar is not None:
-                    dist.all_reduce(ar)
+                    allreduce(ar)
             outs[0] = stream_y
             return
         y = None
@@ -210,7 +226,7 @@ def run_gbxq(args):
             if len(ms) == 1:
                 y = ms[0](xbuf[ms[0].input_dims])
                 if world > 1 and p in ("o_proj", "down_proj"):
-                    dist.all_reduce(y)
+                    allreduce(y)
             else:
                 y = ops.quantized_matmul_grouped(xbuf[ms[0].input_dims], ms)[0]
         outs[0] = y
@@ -300,9 +316,17 @@ def run_gbxq(args):
         except Exception:
             traffic = None
 
-    if rank != 0:
+    def finish():
+        # NCCL teardown with a captured graph alive was seen to hang on the box (profiles/README.md, r01j): make sure
+        # every rank is done, then leave without destroy_process_group
         if world > 1:
-            dist.destroy_process_group()
+            sys.stdout.flush()
+            dist.barrier()
+            torch.cuda.synchronize()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -312,7 +336,7 @@ def run_gbxq(args):
             "workload": f"{args.model} layer-mix {args.strategy} decode batch {M}: {len(full_plan)} QuantizedLinear "
                         f"forwards/step (stored bpw {W.stored_bpw(full_plan):.3f})",
             "bytes_per_step": bytes_step, "l2": "inputs larger than L2 (weights per step >> 126 MB)",
-            "parallelism": f"tp{world}" if world > 1 else "single", "launch": "cuda_graph",
+            "parallelism": f"tp{world}" if world > 1 else "single", "launch": "cuda_graph", "allreduce": ar_kind,
             "calls_per_step": len(calls), "grouped_qkv_gate_up": bool(args.grouped),
             "chain_launch": ({"launches_per_step": len(chains), **chains[0][0].info} if args.stream else None),
         },
@@ -332,8 +356,7 @@ def run_gbxq(args):
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_sample(args, layers_for_cpu=[(p, m) for (p, m) in layers[:7]], M=M, budget_s=args.cpu_seconds)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
@@ -429,6 +452,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--grouped", type=int, default=1, help="1: q|k|v and gate|up as one gbxq_qmm_grouped call each (as the model does)")
     ap.add_argument("--stream", type=int, default=0, help="1: the step's calls as one persistent chain launch (gbxq_qmm_stream); 0: one launch per call")
+    ap.add_argument("--allreduce", default="oneshot", choices=["oneshot", "nccl"], help="row-parallel epilogue under TP")
     ap.add_argument("--pdl", type=int, default=2, help="GBXQ_OPT_PDL (0 plain launches, 1 PDL, 2 PDL + early weight streaming)")
     args = ap.parse_args()
     if args.impl == "reference":

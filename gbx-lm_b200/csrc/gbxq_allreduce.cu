@@ -37,6 +37,12 @@ __global__ void __launch_bounds__(256) allreduce_oneshot_kernel(const T* __restr
     const int64_t v0 = (int64_t)blockIdx.x * per_cta;
     int64_t v1 = v0 + per_cta;
     if (v1 > nvec) v1 = nvec;
+    // seq == 0: the sequence number lives on the device (own flag array, entry world*GBXQ_AR_MAX_CTAS; entry +1 counts
+    // the CTAs that are done), so that a CUDA graph can replay the call: every CTA reads it at entry, the last CTA to
+    // finish advances it.  The launch is plain stream-ordered, so the next call sees the advanced value.
+    uint32_t* local = peer_flags[rank] + world * GBXQ_AR_MAX_CTAS;
+    const bool dev_seq = seq == 0u;
+    if (dev_seq) seq = *reinterpret_cast<volatile uint32_t*>(local) + 1u;
     const int64_t half = (int64_t)(seq & 1u) * half_elems;
 
     // 1. stage own slice
@@ -70,6 +76,16 @@ __global__ void __launch_bounds__(256) allreduce_oneshot_kernel(const T* __restr
 #pragma unroll
         for (int e = 0; e < VEC; e++) ov[e] = from_f32<T>(acc[e]);
         reinterpret_cast<uint4*>(out)[v] = o;
+    }
+    if (dev_seq) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t old = atomicAdd(local + 1, 1u);
+            if (old == gridDim.x - 1u) {
+                local[1] = 0u;
+                *reinterpret_cast<volatile uint32_t*>(local) = seq;
+            }
+        }
     }
 }
 

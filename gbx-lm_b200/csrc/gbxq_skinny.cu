@@ -80,6 +80,7 @@ struct SkinnyParams {
     int nbox;              // 128-byte-wide TMA boxes per row piece
     uint32_t sb_off;       // offset of the scale box inside a ring slot (bias box follows at + rs*32)
     uint32_t slot_bytes;
+    int early_weights;     // 1: parameters are frozen -> the producer streams them before griddepcontrol.wait (GBXQ_OPT_PDL 2)
 };
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0, int c1, uint64_t* bar) {
@@ -134,10 +135,14 @@ skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         fence_mbar_init();
     }
     __syncthreads();
+    // programmatic dependent launch, as in the mmv8 kernels: the next kernel of the stream may become resident now;
+    // x and y are touched only after griddepcontrol.wait (a no-op for plain launches)
+    if (threadIdx.x == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == kWarps) {
         // ===================== producer: a handful of TMA boxes per stage =====================
         if (lane == 0) {
+            if (!p.early_weights) asm volatile("griddepcontrol.wait;" ::: "memory");
             const uint32_t box_bytes = (uint32_t)p.rs * 128u;
             for (int it = 0; it < ns; it++) {
                 const int s = it % kStages;
@@ -160,6 +165,7 @@ skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         // ===================== consumer warps =====================
         const int g = lane >> 2, t = lane & 3;
         const uint32_t ring_u32 = smem_u32(ring);
+        asm volatile("griddepcontrol.wait;" ::: "memory");  // x (and y) belong to the previous kernels of the stream
 
         struct Pre {            // per-stage operands fetched one stage ahead
             uint4 xn[(CQ * 2 + 15) / 16];  // this thread's quarter of token g, natural order (CQ bf16)
@@ -408,9 +414,19 @@ int launch_inst2(const CUtensorMap& tw, const CUtensorMap& ts, const CUtensorMap
         if (e != cudaSuccess) return check_cuda(e);
         configured = true;
     }
-    skinny_kernel<BITS, QW, SB_TMA><<<grid, kThreads, smem, st>>>(tw, ts, tb, p);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = mmv_get_pdl_mode() > 0 ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, skinny_kernel<BITS, QW, SB_TMA>, tw, ts, tb, p);
     count_launch();
-    return check_cuda(cudaGetLastError());
+    return check_cuda(e);
 }
 
 template <int BITS, int QW>
@@ -450,6 +466,7 @@ int launch_skinny(const void* x, const uint32_t* w, const void* s, const void* b
     p.nbox = pl.nbox;
     p.sb_off = pl.sb_off;
     p.slot_bytes = pl.slot;
+    p.early_weights = mmv_get_pdl_mode() >= 2 ? 1 : 0;
     CUtensorMap tw, ts, tb;
     memset(&ts, 0, sizeof(ts));
     memset(&tb, 0, sizeof(tb));

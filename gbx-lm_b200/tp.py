@@ -119,7 +119,8 @@ class OneShotAllReduce:
         self.capacity = capacity_elems
         self.buf = symm.empty((capacity_elems,), dtype=dtype, device=device)
         self.hdl = symm.rendezvous(self.buf, self.group.group_name)
-        self.flags = symm.empty((self.world * _lib.AR_MAX_CTAS,), dtype=torch.int32, device=device)
+        # + 2: device-resident sequence number and CTA counter (seq = 0 mode: CUDA-graph replayable)
+        self.flags = symm.empty((self.world * _lib.AR_MAX_CTAS + 2,), dtype=torch.int32, device=device)
         self.flags.zero_()
         self.fhdl = symm.rendezvous(self.flags, self.group.group_name)
         bufs = [self.hdl.buffer_ptrs[r] for r in range(self.world)]
@@ -136,13 +137,13 @@ class OneShotAllReduce:
     def __call__(self, y: torch.Tensor) -> torch.Tensor:
         from . import _lib
 
-        y = y.contiguous()
-        self.seq += 1
+        if not y.is_contiguous():
+            raise ValueError("OneShotAllReduce reduces in place: y must be contiguous")
         dt = {torch.bfloat16: 0, torch.float16: 1, torch.float32: 2}[y.dtype]
         st = torch.cuda.current_stream().cuda_stream
         rc = _lib.get().gbxq_allreduce_oneshot(
             y.data_ptr(), y.data_ptr(), y.numel(), dt, self.bufs_dev.data_ptr(), self.flags_dev.data_ptr(),
-            self.capacity, self.rank, self.world, self.seq, st,
+            self.capacity, self.rank, self.world, 0, st,
         )
         _lib.check(rc, "gbxq_allreduce_oneshot")
         return y

@@ -208,7 +208,9 @@ uint64_t gbxq_launch_count(void);
  *                    world * GBXQ_AR_MAX_CTAS entries, zero-initialised once.
  *   in  : this rank's partial sums          out: reduced result (rank-order sum, identical on
  *                                                every rank), may alias `in`
- *   seq : starts at 1, increases by exactly 1 per call, same on every rank.
+ *   seq : starts at 1, increases by exactly 1 per call, same on every rank; or 0 on every call: the sequence
+ *         number is then kept on the device in entry world*GBXQ_AR_MAX_CTAS of this rank's flag array (flag arrays
+ *         need world*GBXQ_AR_MAX_CTAS + 2 entries), which makes the call replayable from a CUDA graph.
  * Every rank must enqueue the call with the same count/dtype/seq on a stream of its own device.
  */
 #define GBXQ_AR_MAX_CTAS 32
