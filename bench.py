@@ -142,6 +142,9 @@ def run_gbxq(args):
     # row-parallel epilogue: one-shot NVLink all-reduce over peer memory (gbxq_allreduce_oneshot; 8 KB .. 1 MB decode
     # messages are latency-bound) unless --allreduce nccl, or symmetric memory cannot be set up on this box
     allreduce, ar_kind = None, "none"
+    from gbx_lm_b200 import workloads as _W
+
+    dims_hidden = _W.MODELS[args.model].hidden
     if world > 1:
         ar_kind = "nccl"
         if args.allreduce == "oneshot":
@@ -149,159 +152,200 @@ def run_gbxq(args):
                 from gbx_lm_b200.tp import OneShotAllReduce
 
                 allreduce = OneShotAllReduce(None, dev, capacity_elems=max(1 << 16, 4 * args.batch * 8192))
+                # self-check against NCCL on a random vector, twice (both staging halves), before trusting it
+                for i in range(2):
+                    t = torch.randn(args.batch * dims_hidden, generator=torch.Generator(device=dev).manual_seed(7 * rank + i), device=dev).to(torch.bfloat16)
+                    want = t.float()
+                    dist.all_reduce(want)
+                    got = allreduce(t.clone()).float()
+                    if not torch.allclose(got, want, rtol=2e-2, atol=2e-2):
+                        raise RuntimeError("one-shot all-reduce self-check failed")
                 ar_kind = "gbxq_allreduce_oneshot (peer memory over NVLink)"
             except Exception as e:  # noqa: BLE001
+                allreduce = None
                 ar_kind = f"nccl (one-shot unavailable: {type(e).__name__}: {str(e)[:80]})"
         if allreduce is None:
             allreduce = lambda t: dist.all_reduce(t)  # noqa: E731
 
     ops.set_pdl_mode(args.pdl)
-    dims, plan = build_plan(args)
-    full_plan = plan
-    plan = shard_plan(plan, world) if world > 1 else plan
+    dims, full_plan = build_plan(args)
     M = args.batch
+    # --parallelism: how N > 1 GPUs are used.  tp = tensor-parallel shards of ONE model instance (column-parallel
+    # q/k/v/gate/up, row-parallel o/down + sum all-reduce; strong scaling) -- what the 32B / 70B configurations need;
+    # dp = one full model replica per GPU, independent decode streams, no data-path collective (weak scaling) -- the
+    # deployment of a model that fits one GPU.  auto: dp for <= 8B, tp above.  At N > 1 the other mode is measured
+    # as well and reported under "also".
+    mode = args.parallelism
+    if mode == "auto":
+        mode = "tp" if args.model in ("qwen2.5-32b", "llama-3-70b") else "dp"
+    if world == 1:
+        mode = "single"
 
-    # ---- synthetic weights created directly in HBM (seeded); SURVEY.md 8d recipe
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    layers = []
-    for (i, p, n, k, b, g) in plan:
-        m = QuantizedLinear(k, n, bias=False, group_size=g, bits=b)
-        nb = (1 << b) - 1
-        qw = torch.randint(-(2 ** 31), 2 ** 31 - 1, (n, k * b // 32), generator=gen, device=dev, dtype=torch.int64).to(torch.int32).view(torch.uint32)
-        s = ((torch.rand((n, k // g), generator=gen, device=dev) + 0.5) * (2.0 / (k ** 0.5) / nb)).to(torch.bfloat16)
-        eps = torch.rand((n, k // g), generator=gen, device=dev) * 0.1 - 0.05
-        z = (-s.float() * (nb / 2.0) * (1.0 + eps)).to(torch.bfloat16)
-        m._set("qweight", qw)
-        m._set("scales", s)
-        m._set("zeros", z)
-        m._set("channel_scale", None)
-        layers.append((p, m))
-    xbuf = {}
-    for (_, _, n, k, _, _) in plan:
-        if k not in xbuf:
-            xbuf[k] = torch.randn((M, k), generator=gen, device=dev).to(torch.bfloat16)
-    h_in = torch.randn((M, dims.hidden)).to(torch.bfloat16).pin_memory()
-    h_out = torch.empty((M, dims.hidden), dtype=torch.bfloat16).pin_memory()
-    x_hidden = xbuf[dims.hidden]
+    def measure(tp: int):
+        plan = shard_plan(full_plan, tp) if tp > 1 else full_plan
 
-    outs = [None]
+        # ---- synthetic weights created directly in HBM (seeded); SURVEY.md 8d recipe
+        gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+        layers = []
+        for (i, p, n, k, b, g) in plan:
+            m = QuantizedLinear(k, n, bias=False, group_size=g, bits=b)
+            nb = (1 << b) - 1
+            qw = torch.randint(-(2 ** 31), 2 ** 31 - 1, (n, k * b // 32), generator=gen, device=dev, dtype=torch.int64).to(torch.int32).view(torch.uint32)
+            s = ((torch.rand((n, k // g), generator=gen, device=dev) + 0.5) * (2.0 / (k ** 0.5) / nb)).to(torch.bfloat16)
+            eps = torch.rand((n, k // g), generator=gen, device=dev) * 0.1 - 0.05
+            z = (-s.float() * (nb / 2.0) * (1.0 + eps)).to(torch.bfloat16)
+            m._set("qweight", qw)
+            m._set("scales", s)
+            m._set("zeros", z)
+            m._set("channel_scale", None)
+            layers.append((p, m))
+        xbuf = {}
+        for (_, _, n, k, _, _) in plan:
+            if k not in xbuf:
+                xbuf[k] = torch.randn((M, k), generator=gen, device=dev).to(torch.bfloat16)
+        h_in = torch.randn((M, dims.hidden)).to(torch.bfloat16).pin_memory()
+        h_out = torch.empty((M, dims.hidden), dtype=torch.bfloat16).pin_memory()
+        x_hidden = xbuf[dims.hidden]
 
-    # the callers' launch structure (gbx_lm/models/qllama.py:76,115): q|k|v and gate|up read the same activations
-    # and go out as ONE grouped call each, o_proj and down_proj as single calls -> 4 library calls per block
-    calls, i = [], 0
-    while i < len(layers):
-        names = [p for p, _ in layers[i:i + 3]]
-        if args.grouped and names == ["q_proj", "k_proj", "v_proj"]:
-            calls.append(("qkv", [m for _, m in layers[i:i + 3]])); i += 3
-        elif args.grouped and names[:2] == ["gate_proj", "up_proj"]:
-            calls.append(("gate_up", [m for _, m in layers[i:i + 2]])); i += 2
-        else:
-            calls.append((layers[i][0], [layers[i][1]])); i += 1
+        outs = [None]
 
-    # --stream 1: the calls of a step as a chain executed by ONE persistent launch (gbxq_qmm_stream), every call
-    # ordered after the one before it (dep = previous: exactly the semantics of the launch-per-call step below).
-    # Under TP the chain is cut at each all-reduce (after o_proj / down_proj).
-    chains = []
-    if args.stream:
-        cur = ops.StreamChain(M)
-        for p, ms in calls:
-            ys = cur.add(xbuf[ms[0].input_dims], ms)
-            if world > 1 and p in ("o_proj", "down_proj"):
-                chains.append((cur.finalize(), ys[0]))
-                cur = ops.StreamChain(M)
-        if len(cur):
-            chains.append((cur.finalize(), None))
-        stream_y = ys[0]
-
-    def step():
-        if args.stream:
-            for ch, ar in chains:
-                ch.run()
-                if ar is not None:
-                    allreduce(ar)
-            outs[0] = stream_y
-            return
-        y = None
-        for p, ms in calls:
-            if len(ms) == 1:
-                y = ms[0](xbuf[ms[0].input_dims])
-                if world > 1 and p in ("o_proj", "down_proj"):
-                    allreduce(y)
+        # the callers' launch structure (gbx_lm/models/qllama.py:76,115): q|k|v and gate|up read the same activations
+        # and go out as ONE grouped call each, o_proj and down_proj as single calls -> 4 library calls per block
+        calls, i = [], 0
+        while i < len(layers):
+            names = [p for p, _ in layers[i:i + 3]]
+            if args.grouped and names == ["q_proj", "k_proj", "v_proj"]:
+                calls.append(("qkv", [m for _, m in layers[i:i + 3]])); i += 3
+            elif args.grouped and names[:2] == ["gate_proj", "up_proj"]:
+                calls.append(("gate_up", [m for _, m in layers[i:i + 2]])); i += 2
             else:
-                y = ops.quantized_matmul_grouped(xbuf[ms[0].input_dims], ms)[0]
-        outs[0] = y
+                calls.append((layers[i][0], [layers[i][1]])); i += 1
 
-    # ---- warm-up eagerly (also sets kernel attributes), then capture one step into a CUDA graph
-    s = torch.cuda.Stream()
-    s.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(s):
-        step()
-        step()
-    torch.cuda.current_stream().wait_stream(s)
-    torch.cuda.synchronize()
-    n0 = ops.launch_count()
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
-        step()
-    launches_per_step = ops.launch_count() - n0
-    y_last = outs[0]
+        # --stream 1: the calls of a step as a chain executed by ONE persistent launch (gbxq_qmm_stream), every call
+        # ordered after the one before it (dep = previous: exactly the semantics of the launch-per-call step below).
+        # Under TP the chain is cut at each all-reduce (after o_proj / down_proj).
+        chains = []
+        if args.stream:
+            cur = ops.StreamChain(M)
+            for p, ms in calls:
+                ys = cur.add(xbuf[ms[0].input_dims], ms)
+                if tp > 1 and p in ("o_proj", "down_proj"):
+                    chains.append((cur.finalize(), ys[0]))
+                    cur = ops.StreamChain(M)
+            if len(cur):
+                chains.append((cur.finalize(), None))
+            stream_y = ys[0]
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
+        def step():
+            if args.stream:
+                for ch, ar in chains:
+                    ch.run()
+                    if ar is not None:
+                        allreduce(ar)
+                outs[0] = stream_y
+                return
+            y = None
+            for p, ms in calls:
+                if len(ms) == 1:
+                    y = ms[0](xbuf[ms[0].input_dims])
+                    if tp > 1 and p in ("o_proj", "down_proj"):
+                        allreduce(y)
+                else:
+                    y = ops.quantized_matmul_grouped(xbuf[ms[0].input_dims], ms)[0]
+            outs[0] = y
+
+        # ---- warm-up eagerly (also sets kernel attributes), then capture one step into a CUDA graph
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            step()
+            step()
+        torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        n0 = ops.launch_count()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step()
+        launches_per_step = ops.launch_count() - n0
+        y_last = outs[0]
 
-    for _ in range(max(args.warmup, 3)):
-        graph.replay()
-    barrier()
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
 
-    # ---- timed region: EXACTLY K steps, CUDA events on the launching stream, max over ranks
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.25)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        graph.replay()
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    if args.stream and any(ch.timed_out() for ch, _ in chains):
-        raise SystemExit("gbxq_qmm_stream: a CTA gave up waiting (grid not co-resident); the measurement is void")
+        for _ in range(max(args.warmup, 3)):
+            graph.replay()
+        barrier()
 
-    # ---- e2e: the same step through the public API with HOST buffers (pinned), copies inside the timed region
-    def e2e_step():
-        x_hidden.copy_(h_in, non_blocking=True)
-        graph.replay()
-        h_out.copy_(y_last if y_last.shape == h_out.shape else y_last[:, : dims.hidden], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        # ---- timed region: EXACTLY K steps, CUDA events on the launching stream, max over ranks
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+            time.sleep(0.25)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            graph.replay()
+        e1.record()
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+        if world > 1:
+            t = torch.tensor([ms_total], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_total = float(t.item())
+        ms_step = ms_total / args.steps
+        if args.stream and any(ch.timed_out() for ch, _ in chains):
+            raise SystemExit("gbxq_qmm_stream: a CTA gave up waiting (grid not co-resident); the measurement is void")
 
-    for _ in range(3):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for _ in range(args.steps):
-        e2e_step()
-    f1.record()
-    barrier()
-    e2e_wall = (time.perf_counter() - t0) * 1e3 / args.steps
-    e2e_ms = max(f0.elapsed_time(f1) / args.steps, e2e_wall)  # host-visible time per step (>= device time)
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+        # ---- e2e: the same step through the public API with HOST buffers (pinned), copies inside the timed region
+        def e2e_step():
+            x_hidden.copy_(h_in, non_blocking=True)
+            graph.replay()
+            h_out.copy_(y_last if y_last.shape == h_out.shape else y_last[:, : dims.hidden], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
 
-    bytes_step = sum(W.qmm_bytes(M, n, k, b, g) for (_, _, n, k, b, g) in full_plan)
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        f1.record()
+        barrier()
+        e2e_wall = (time.perf_counter() - t0) * 1e3 / args.steps
+        e2e_ms = max(f0.elapsed_time(f1) / args.steps, e2e_wall)  # host-visible time per step (>= device time)
+        if world > 1:
+            t = torch.tensor([e2e_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+
+        return {"ms_step": ms_step, "e2e_ms": e2e_ms, "e2e_wall": e2e_wall, "launches_per_step": launches_per_step,
+                "calls": len(calls), "plan": plan, "layers": layers, "clocks": clocks, "chains": chains,
+                "h2d": int(h_in.numel() * 2), "d2h": int(h_out.numel() * 2)}
+
+    r = measure(world if mode == "tp" else 1)
+    ms_step, e2e_ms, e2e_wall, launches_per_step, plan, layers, clocks, chains = (
+        r["ms_step"], r["e2e_ms"], r["e2e_wall"], r["launches_per_step"], r["plan"], r["layers"], r["clocks"], r["chains"])
+    ncalls, r_h2d, r_d2h = r["calls"], r["h2d"], r["d2h"]
+    replicas = world if mode == "dp" else 1
+    also = None
+    if world > 1 and not args.no_also:
+        del r
+        r2 = measure(1 if mode == "tp" else world)
+        other = "dp" if mode == "tp" else "tp"
+        rep2 = world if other == "dp" else 1
+        b2 = sum(W.qmm_bytes(M, n, k, b, g) for (_, _, n, k, b, g) in full_plan) * rep2
+        also = {"parallelism": f"{other}{world}", "scaling": "weak" if other == "dp" else "strong",
+                "value": round(b2 / (r2["ms_step"] * 1e-3) / 1e9, 2), "unit": UNIT, "ms_per_step": round(r2["ms_step"], 5),
+                "decode_tok_s_qmm_only": round(1e3 / r2["ms_step"] * M * rep2, 2)}
+        del r2
+
+    bytes_step = sum(W.qmm_bytes(M, n, k, b, g) for (_, _, n, k, b, g) in full_plan) * replicas
     value = bytes_step / (ms_step * 1e-3) / 1e9
     peak, peak_src = load_peaks()
     # roofline of the dominant kernel (the streaming GEMV: every launch of the timed region is one):
@@ -331,16 +375,17 @@ def run_gbxq(args):
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 5), "higher_is_better": True,
-        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "scaling": "strong" if mode == "tp" else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {
             "workload": f"{args.model} layer-mix {args.strategy} decode batch {M}: {len(full_plan)} QuantizedLinear "
                         f"forwards/step (stored bpw {W.stored_bpw(full_plan):.3f})",
             "bytes_per_step": bytes_step, "l2": "inputs larger than L2 (weights per step >> 126 MB)",
-            "parallelism": f"tp{world}" if world > 1 else "single", "launch": "cuda_graph", "allreduce": ar_kind,
-            "calls_per_step": len(calls), "grouped_qkv_gate_up": bool(args.grouped),
+            "parallelism": f"{mode}{world}" if world > 1 else "single", "launch": "cuda_graph",
+            "allreduce": ar_kind if mode == "tp" else "none (independent replicas)" if world > 1 else "none",
+            "calls_per_step": ncalls, "grouped_qkv_gate_up": bool(args.grouped),
             "chain_launch": ({"launches_per_step": len(chains), **chains[0][0].info} if args.stream else None),
         },
-        "decode_tok_s_qmm_only": round(1e3 / ms_step * M, 2),
+        "decode_tok_s_qmm_only": round(1e3 / ms_step * M * replicas, 2),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                      "kernel": ("gbxq::stream_kernel (persistent chain launch: the mmv8 body over every call of the step)"
@@ -348,9 +393,10 @@ def run_gbxq(args):
                      "bytes_per_launch_avg": rank_bytes // max(launches_per_step, 1),
                      "avg_launch_us": round(ms_step * 1e3 / max(launches_per_step, 1), 3)},
         "e2e": {"value": round(bytes_step / (e2e_ms * 1e-3) / 1e9, 2), "unit": UNIT,
-                "h2d_bytes_per_step": int(h_in.numel() * 2), "d2h_bytes_per_step": int(h_out.numel() * 2),
+                "h2d_bytes_per_step": r_h2d * replicas, "d2h_bytes_per_step": r_d2h * replicas,
                 "ms_per_step": round(e2e_ms, 5), "wall_ms_per_step": round(e2e_wall, 5)},
         "gpu_launches": int(launches_per_step * args.steps),
+        "also": also,
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -452,6 +498,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--grouped", type=int, default=1, help="1: q|k|v and gate|up as one gbxq_qmm_grouped call each (as the model does)")
     ap.add_argument("--stream", type=int, default=0, help="1: the step's calls as one persistent chain launch (gbxq_qmm_stream); 0: one launch per call")
+    ap.add_argument("--parallelism", default="auto", choices=["auto", "tp", "dp"], help="N > 1: tensor-parallel shards or independent replicas")
+    ap.add_argument("--no-also", action="store_true", help="N > 1: skip the measurement of the other parallelism mode")
     ap.add_argument("--allreduce", default="oneshot", choices=["oneshot", "nccl"], help="row-parallel epilogue under TP")
     ap.add_argument("--pdl", type=int, default=2, help="GBXQ_OPT_PDL (0 plain launches, 1 PDL, 2 PDL + early weight streaming)")
     args = ap.parse_args()
