@@ -30,6 +30,10 @@ EXPORTS = (
     "gbxq_set_option",
     "gbxq_get_option",
     "gbxq_allreduce_oneshot",
+    "gbxq_rope_cache",
+    "gbxq_decode_attention",
+    "gbxq_add_rmsnorm",
+    "gbxq_silu_mul",
 )
 
 
@@ -118,6 +122,15 @@ def get() -> ctypes.CDLL:
     lib.gbxq_set_option.argtypes = [ci, ci]
     lib.gbxq_get_option.restype = ci
     lib.gbxq_get_option.argtypes = [ci]
+    cf = ctypes.c_float
+    lib.gbxq_rope_cache.restype = ci
+    lib.gbxq_rope_cache.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, i64, vp]
+    lib.gbxq_decode_attention.restype = ci
+    lib.gbxq_decode_attention.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, i64, i64, cf, vp]
+    lib.gbxq_add_rmsnorm.restype = ci
+    lib.gbxq_add_rmsnorm.argtypes = [vp, vp, vp, cf, vp, vp, i64, ci, vp]
+    lib.gbxq_silu_mul.restype = ci
+    lib.gbxq_silu_mul.argtypes = [vp, vp, vp, i64, vp]
     lib.gbxq_allreduce_oneshot.restype = ci
     lib.gbxq_allreduce_oneshot.argtypes = [vp, vp, i64, ci, vp, vp, i64, ci, ci, u32, vp]
     if lib.gbxq_abi_version() != 1:

@@ -26,6 +26,7 @@ SOURCES = [
     "gbxq_mmv8.cu",
     "gbxq_mmv8_grouped.cu",
     "gbxq_stream.cu",
+    "gbxq_glue.cu",
     "gbxq_gemm_sm100.cu",
     "gbxq_allreduce.cu",
 ]

@@ -201,6 +201,32 @@ int gbxq_dequantize(const uint32_t* qweight, const void* scales, const void* bia
     return launch_dequantize(qweight, scales, biases, w_out, N, K, bits, group_size, dtype, (cudaStream_t)stream);
 }
 
+int gbxq_rope_cache(void* q, const void* k, const void* v, const int64_t* pos_dev, const float* inv_freq_dev, void* k_cache,
+                    void* v_cache, int B, int Hq, int Hkv, int D, int64_t max_len, void* stream) {
+    if (!q || !k || !v || !pos_dev || !inv_freq_dev || !k_cache || !v_cache) return GBXQ_ENULL;
+    return launch_rope_cache(q, k, v, pos_dev, inv_freq_dev, k_cache, v_cache, B, Hq, Hkv, D, max_len, (cudaStream_t)stream);
+}
+
+int gbxq_decode_attention(const void* q, const void* k_cache, const void* v_cache, const int64_t* pos_dev, void* out, int B,
+                          int Hq, int Hkv, int D, int64_t max_len, int64_t attend_len, float scale, void* stream) {
+    if (!q || !k_cache || !v_cache || !pos_dev || !out) return GBXQ_ENULL;
+    return launch_decode_attention(q, k_cache, v_cache, pos_dev, out, B, Hq, Hkv, D, max_len, attend_len, scale,
+                                   (cudaStream_t)stream);
+}
+
+int gbxq_add_rmsnorm(const void* x, const void* r, const void* w, float eps, void* h_out, void* y_out, int64_t rows, int H,
+                     void* stream) {
+    if (!x || !w || !y_out) return GBXQ_ENULL;
+    if (((uintptr_t)x | (uintptr_t)r | (uintptr_t)w | (uintptr_t)h_out | (uintptr_t)y_out) & 15) return GBXQ_EALIGN;
+    return launch_add_rmsnorm(x, r, w, eps, h_out, y_out, rows, H, (cudaStream_t)stream);
+}
+
+int gbxq_silu_mul(const void* gate, const void* up, void* out, int64_t n, void* stream) {
+    if (!gate || !up || !out) return GBXQ_ENULL;
+    if (((uintptr_t)gate | (uintptr_t)up | (uintptr_t)out) & 15) return GBXQ_EALIGN;
+    return launch_silu_mul(gate, up, out, n, (cudaStream_t)stream);
+}
+
 int gbxq_allreduce_oneshot(const void* in, void* out, int64_t count, int dtype, void* const* peer_bufs_dev,
                            uint32_t* const* peer_flags_dev, int64_t capacity, int rank, int world, uint32_t seq,
                            void* stream) {

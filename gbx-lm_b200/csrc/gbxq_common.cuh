@@ -173,6 +173,13 @@ int stream_plan(const gbxq_stream_call* calls, int ncalls, int64_t M, int dtype,
                 gbxq_stream_info* info);
 void stream_debug_patch(void* host_blob, int ncalls, unsigned long long* dbg_dev);
 int launch_stream(const gbxq_stream_info* info, const void* blob, void* counters, cudaStream_t st);
+int launch_rope_cache(void* q, const void* k, const void* v, const int64_t* pos, const float* inv_freq, void* kc, void* vc,
+                      int B, int Hq, int Hkv, int D, int64_t max_len, cudaStream_t st);
+int launch_decode_attention(const void* q, const void* kc, const void* vc, const int64_t* pos, void* out, int B, int Hq,
+                            int Hkv, int D, int64_t max_len, int64_t attend_len, float scale, cudaStream_t st);
+int launch_add_rmsnorm(const void* x, const void* r, const void* w, float eps, void* h_out, void* y_out, int64_t rows, int H,
+                       cudaStream_t st);
+int launch_silu_mul(const void* g, const void* u, void* out, int64_t n, cudaStream_t st);
 void mmv_set_pdl_mode(int mode);
 int mmv_get_pdl_mode();
 bool gemm_supported(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype, const void* x, const void* w,

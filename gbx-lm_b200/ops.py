@@ -347,6 +347,74 @@ class StreamChain:
         return bool(self._counters[-1].item())
 
 
+# ------------------------------------------------------------------------------------------ decode-step glue
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _bf16c(*ts):
+    for t in ts:
+        if t is not None and (t.dtype != torch.bfloat16 or not t.is_contiguous() or not t.is_cuda):
+            raise ValueError("decode glue ops take contiguous CUDA bf16 tensors")
+
+
+def rope_cache(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, position: torch.Tensor, inv_freq: torch.Tensor,
+               k_cache: torch.Tensor, v_cache: torch.Tensor) -> torch.Tensor:
+    """gbxq_rope_cache: q [B,Hq,D] rotated IN PLACE (returned), k rotated and v copied into the caches [B,Hkv,max_len,D] at
+    `position` (int64 device tensor [1]).  Replaces RoPE + cache.update of a decode step (gbx_lm/models/qllama.py:83-88)."""
+    _bf16c(q, k, v, k_cache, v_cache)
+    b, hq, d = q.shape
+    hkv, max_len = k_cache.shape[1], k_cache.shape[2]
+    if position.dtype != torch.int64 or inv_freq.dtype != torch.float32 or inv_freq.numel() != d // 2:
+        raise ValueError("rope_cache: position int64 [1], inv_freq float32 [D/2]")
+    with torch.cuda.device(q.device):
+        rc = _lib.get().gbxq_rope_cache(q.data_ptr(), k.data_ptr(), v.data_ptr(), position.data_ptr(), inv_freq.data_ptr(),
+                                        k_cache.data_ptr(), v_cache.data_ptr(), b, hq, hkv, d, max_len, _stream())
+    _lib.check(rc, "gbxq_rope_cache")
+    return q
+
+
+def decode_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, position: torch.Tensor, scale: float,
+                     attend_len: Optional[int] = None) -> torch.Tensor:
+    """gbxq_decode_attention: one query row per head, q [B,Hq,D], against the static caches, keys 0..position visible
+    (and < attend_len), GQA.  Returns [B,Hq,D].  Replaces mask + scaled_dot_product_attention (qllama.py:90-93)."""
+    _bf16c(q, k_cache, v_cache)
+    b, hq, d = q.shape
+    hkv, max_len = k_cache.shape[1], k_cache.shape[2]
+    out = torch.empty_like(q)
+    with torch.cuda.device(q.device):
+        rc = _lib.get().gbxq_decode_attention(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), position.data_ptr(),
+                                              out.data_ptr(), b, hq, hkv, d, max_len, int(attend_len or max_len), float(scale),
+                                              _stream())
+    _lib.check(rc, "gbxq_decode_attention")
+    return out
+
+
+def add_rmsnorm(x: torch.Tensor, r: Optional[torch.Tensor], w: torch.Tensor, eps: float, want_h: bool = True):
+    """gbxq_add_rmsnorm: h = x + r (r None: h = x), y = RMSNorm(h) * w over the last dimension.  Returns (h, y); h is None
+    when want_h is False.  Replaces the residual add + nn.RMSNorm pair (qllama.py:137-141)."""
+    _bf16c(x, r, w)
+    hdim = x.shape[-1]
+    rows = x.numel() // hdim
+    y = torch.empty_like(x)
+    h = torch.empty_like(x) if (want_h and r is not None) else None
+    with torch.cuda.device(x.device):
+        rc = _lib.get().gbxq_add_rmsnorm(x.data_ptr(), r.data_ptr() if r is not None else None, w.data_ptr(), float(eps),
+                                         h.data_ptr() if h is not None else None, y.data_ptr(), rows, hdim, _stream())
+    _lib.check(rc, "gbxq_add_rmsnorm")
+    return (h if r is not None else (x if want_h else None)), y
+
+
+def silu_mul(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
+    """gbxq_silu_mul: silu(gate) * up (qllama.py:115), both roundings of the unfused expression kept."""
+    _bf16c(gate, up)
+    out = torch.empty_like(gate)
+    with torch.cuda.device(gate.device):
+        rc = _lib.get().gbxq_silu_mul(gate.data_ptr(), up.data_ptr(), out.data_ptr(), gate.numel(), _stream())
+    _lib.check(rc, "gbxq_silu_mul")
+    return out
+
+
 def dequantize(w: torch.Tensor, scales: torch.Tensor, biases: torch.Tensor, group_size: int = 64, bits: int = 4) -> torch.Tensor:
     """Drop-in for `mx.dequantize` (bit-exact: T(T(scale*q)+bias), T = scales.dtype)."""
     return _dequantize_op(w, scales, biases, int(group_size), int(bits))

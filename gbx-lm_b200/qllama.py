@@ -6,14 +6,16 @@ reference so a gba2mlx checkpoint loads by key:
     model.layers.N.self_attn.{q,k,v,o}_proj.{qweight,scales,zeros[,bias]},
     model.layers.N.mlp.{gate,up,down}_proj.{qweight,scales,zeros}, model.norm.weight, lm_head.weight
 
-Attention / RoPE / RMSNorm are glue (out of scope as kernels) and use
-PyTorch ops; the seven projections per block go through libgbxq.  Tensor parallelism
+Attention / RoPE / RMSNorm are glue written with PyTorch ops; at DECODE (one new token,
+cache present) the glue of a block runs as four libgbxq launches instead (rope + cache write,
+one-query attention, residual add + RMSNorm, silu * up).  The seven projections per block go through libgbxq.  Tensor parallelism
 (new work): q/k/v/gate/up column-parallel, o/down row-parallel + sum all-reduce.
 """
 from __future__ import annotations
 
 import inspect
 import math
+import os
 from dataclasses import dataclass
 from typing import Any, Dict, List, Optional, Union
 
@@ -84,6 +86,15 @@ def rope_inv_freq(dims: int, base: float, scaling: Optional[dict]) -> torch.Tens
     raise ValueError(f"Unsupported RoPE type {rope_type} (yarn/longrope are outside the configs)")
 
 
+# Decode-step glue through libgbxq (rope_cache / decode_attention / add_rmsnorm / silu_mul) instead of ~45 framework
+# launches per block; GBXQ_FUSED_DECODE=0 keeps the plain torch glue (the tests compare the two).
+FUSED_DECODE = os.environ.get("GBXQ_FUSED_DECODE", "1") != "0"
+
+
+def fused_decode_ok(x: torch.Tensor, L: int, cache) -> bool:
+    return FUSED_DECODE and L == 1 and cache is not None and x.is_cuda and x.dtype == torch.bfloat16
+
+
 class RoPE(nn.Module):
     """Non-traditional (half-split) rotary embedding, like mx.fast.rope(traditional=False)."""
 
@@ -150,6 +161,13 @@ class Attention(nn.Module):  # gbx_lm/models/qllama.py:39-96
         B, L, _ = x.shape
         # one grouped launch for the three projections of x (ref qllama.py:76 calls them back to back)
         q, k, v = ops.quantized_matmul_grouped(x, (self.q_proj, self.k_proj, self.v_proj))
+        if fused_decode_ok(x, L, cache) and self.head_dim in (64, 128):
+            # decode step: RoPE + cache write in one launch, one-query attention in another
+            qh = q.view(B, self.n_heads, self.head_dim)
+            ops.rope_cache(qh, k.view(B, self.n_kv_heads, self.head_dim), v.view(B, self.n_kv_heads, self.head_dim),
+                           positions, self.rope.inv_freq, cache.keys, cache.values)
+            out = ops.decode_attention(qh, cache.keys, cache.values, positions, self.scale, attend_len)
+            return self.tp.all_reduce(self.o_proj(out.view(B, 1, -1)))
         q = q.view(B, L, self.n_heads, -1).transpose(1, 2)
         k = k.view(B, L, self.n_kv_heads, -1).transpose(1, 2)
         v = v.view(B, L, self.n_kv_heads, -1).transpose(1, 2)
@@ -183,7 +201,11 @@ class MLP(nn.Module):  # gbx_lm/models/qllama.py:99-115
 
     def forward(self, x):
         gate, up = ops.quantized_matmul_grouped(x, (self.gate_proj, self.up_proj))  # ref qllama.py:115
-        return self.tp.all_reduce(self.down_proj(F.silu(gate) * up))
+        if gate.is_cuda and gate.dtype == torch.bfloat16 and gate.numel() % 8 == 0 and FUSED_DECODE:
+            act = ops.silu_mul(gate, up)
+        else:
+            act = F.silu(gate) * up
+        return self.tp.all_reduce(self.down_proj(act))
 
 
 class TransformerBlock(nn.Module):  # gbx_lm/models/qllama.py:118-141
@@ -211,6 +233,16 @@ class LlamaModel(nn.Module):  # gbx_lm/models/qllama.py:144-174
         h = self.embed_tokens(inputs)
         if cache is None:
             cache = [None] * len(self.layers)
+        if fused_decode_ok(h, inputs.shape[1], cache[0]) and h.shape[-1] % 8 == 0:
+            # decode step: every residual add travels with the RMSNorm that follows it (one launch each); the add of a
+            # block's MLP output happens in the next block's (or the final) norm launch
+            resid, pend = h.contiguous(), None
+            for layer, c in zip(self.layers, cache):
+                resid, n = ops.add_rmsnorm(resid, pend, layer.input_layernorm.weight, layer.input_layernorm.eps)
+                a = layer.self_attn(n, positions, c, attend_len)
+                resid, n = ops.add_rmsnorm(resid, a, layer.post_attention_layernorm.weight, layer.post_attention_layernorm.eps)
+                pend = layer.mlp(n)
+            return ops.add_rmsnorm(resid, pend, self.norm.weight, self.norm.eps, want_h=False)[1]
         for layer, c in zip(self.layers, cache):
             h = layer(h, positions, c, attend_len)
         return self.norm(h)

@@ -197,6 +197,28 @@ int gbxq_get_option(int key);
 uint64_t gbxq_launch_count(void);
 
 /*
+ * Decode-step glue (the fusions either side of the path).  What the reference's callers do
+ * between the QuantizedLinear forwards of a block at decode (one new token per sequence), as four launches instead of
+ * ~45 framework launches; bf16 tensors, fp32 arithmetic, the step's position read from DEVICE memory so that a CUDA
+ * graph can replay the step.
+ *   gbxq_rope_cache       q[B,Hq,D] rotated in place, k[B,Hkv,D] rotated into k_cache[B,Hkv,max_len,D] at *pos, v copied
+ *                         into v_cache at *pos (mx.fast.rope traditional=False + cache.update_and_fetch,
+ *                         gbx_lm/models/qllama.py:83-88); inv_freq f32 [D/2] already carries the rope scaling
+ *   gbxq_decode_attention out[B,Hq,D] = softmax(scale * q . K[0..min(*pos, attend_len-1)]) . V, GQA by Hq/Hkv
+ *                         (scaled_dot_product_attention, qllama.py:90-93); D = 64 or 128
+ *   gbxq_add_rmsnorm      h = x + r (r NULL: h = x), y = RMSNorm(h) * w; h_out may be NULL or alias x
+ *                         (residual + nn.RMSNorm, qllama.py:137-141)
+ *   gbxq_silu_mul         out = silu(gate) * up (qllama.py:115), n elements, n % 8 == 0
+ */
+int gbxq_rope_cache(void* q, const void* k, const void* v, const int64_t* pos_dev, const float* inv_freq_dev,
+                    void* k_cache, void* v_cache, int B, int Hq, int Hkv, int D, int64_t max_len, void* stream);
+int gbxq_decode_attention(const void* q, const void* k_cache, const void* v_cache, const int64_t* pos_dev, void* out,
+                          int B, int Hq, int Hkv, int D, int64_t max_len, int64_t attend_len, float scale, void* stream);
+int gbxq_add_rmsnorm(const void* x, const void* r, const void* w, float eps, void* h_out, void* y_out, int64_t rows,
+                     int H, void* stream);
+int gbxq_silu_mul(const void* gate, const void* up, void* out, int64_t n, void* stream);
+
+/*
  * Tensor-parallel row-parallel epilogue (new work; the reference has no TP -- SURVEY.md 2.2):
  * one-shot sum all-reduce of a small [count] T vector over peer-mapped buffers on NVLink
  * (P2P loads/stores, no NCCL call).  Meant for the latency-bound decode messages
