@@ -291,6 +291,21 @@ def write_synthetic_checkpoint(path: Union[str, Path], dims, strategy: Optional[
 
 
 # ------------------------------------------------------------------------------------------ decode loop
+def fast_argmax(x: torch.Tensor) -> torch.Tensor:
+    """argmax over the last (vocabulary) dimension, first occurrence on ties like torch.argmax, as two row-parallel
+    reductions: a [B, V] single-row argmax is one slow block on the GPU (~0.5 ms at V = 128256, profiles/README.md), a
+    [B*a, V/a] max followed by an argmax over the a segment maxima is not."""
+    v = x.shape[-1]
+    a = next((c for c in (256, 192, 128, 96, 64, 48, 32) if v % c == 0 and v // c >= 64), 0)
+    if not a:
+        return torch.argmax(x, dim=-1)
+    seg = x.reshape(*x.shape[:-1], a, v // a)
+    m, i = seg.max(dim=-1)              # first maximal index inside every segment
+    j = m.argmax(dim=-1, keepdim=True)  # first segment holding the global maximum
+    return (j * (v // a) + i.gather(-1, j)).squeeze(-1)
+
+
+
 class DecodeGraph:
     """One decode step (token ids [B,1] -> logits) captured in a CUDA graph: the whole step --
     7*L QuantizedLinear launches plus the glue -- replays as one submission."""
@@ -303,9 +318,12 @@ class DecodeGraph:
         self.logits = None
         self.graph = None
 
-    def capture(self, tokens: torch.Tensor, position: int):
+    def capture(self, tokens: torch.Tensor, position: int, device_loop: int = 0):
         """Warm-up + capture at (tokens, position) = the step that will be replayed first, so the KV
-        entries written during warm-up/capture are exactly the ones that step writes anyway."""
+        entries written during warm-up/capture are exactly the ones that step writes anyway.
+        device_loop = n > 0: the greedy sampler is part of the graph -- argmax of the logits (= argmax of the
+        log-probabilities, utils.py:285,305-306), fed back as the next step's token, position advanced and the token
+        appended to `self.out` [n] on the device -- so that n steps replay back to back without a host round trip."""
         self.tok.copy_(tokens.reshape(self.tok.shape))
         self.pos.fill_(position)
         s = torch.cuda.Stream()
@@ -314,9 +332,18 @@ class DecodeGraph:
             for _ in range(2):
                 self.model(self.tok, self.cache, positions=self.pos, attend_len=None)
         torch.cuda.current_stream().wait_stream(s)
+        if device_loop:
+            self.out = torch.zeros((device_loop, self.tok.shape[0]), dtype=torch.long, device=self.tok.device)
+            self.idx = torch.zeros((1,), dtype=torch.long, device=self.tok.device)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph), torch.no_grad():
             self.logits = self.model(self.tok, self.cache, positions=self.pos, attend_len=None)
+            if device_loop:
+                nxt = fast_argmax(self.logits[:, -1, :])  # [B]; bf16 -> fp32 is order preserving, so no cast
+                self.out.index_copy_(0, self.idx, nxt[None])
+                self.tok.copy_(nxt[:, None])
+                self.pos.add_(1)
+                self.idx.add_(1)
         return self
 
     def step(self, tokens: torch.Tensor, position: int) -> torch.Tensor:
@@ -372,6 +399,38 @@ def generate_step(
                 logits = model(tok.reshape(1, 1), cache)[:, -1, :]
             lp = _logprobs(logits)
             tok = sampler(lp)
+
+
+def generate_tokens_device(model, prompt: torch.Tensor, max_tokens: int = 128, prefill_step_size: int = 2048) -> Tuple[List[int], dict]:
+    """Greedy generation with the sampler inside the captured decode step (DecodeGraph device_loop): the same tokens as
+    `generate_tokens` (argmax of the log-probabilities = argmax of the logits), but the host only enqueues replays and
+    reads the tokens once at the end -- the per-token host round trip of utils.py:299-337 (~0.3-0.6 ms on a B200 box)
+    is gone.  Same timing definitions as generate_tokens."""
+    y = prompt.reshape(-1).to(next(model.parameters()).device)
+    n_prompt = y.numel()
+    cache = qllama.make_prompt_cache(model, 1, n_prompt + max_tokens + 1)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        while y.numel() > prefill_step_size:
+            model(y[:prefill_step_size][None], cache)
+            y = y[prefill_step_size:]
+        tok = torch.argmax(model(y[None], cache)[:, -1, :].float(), dim=-1)
+    pos0 = cache[0].offset
+    dg = DecodeGraph(model, cache).capture(tok, pos0, device_loop=max(max_tokens - 1, 1))
+    first = int(tok.item())
+    t_first = time.perf_counter()
+    for _ in range(max_tokens - 1):
+        dg.graph.replay()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    toks = [first] + [int(t) for t in dg.out[: max_tokens - 1, 0].tolist()]
+    for c in cache:
+        c.offset = pos0 + max_tokens - 1
+    stats = {
+        "prompt_tokens": int(n_prompt), "prompt_tps": n_prompt / max(t_first - t0, 1e-9),
+        "generation_tokens": len(toks), "generation_tps": max(len(toks) - 1, 1) / max(t1 - t_first, 1e-9),
+    }
+    return toks, stats
 
 
 def generate_tokens(model, prompt: torch.Tensor, max_tokens: int = 128, **kw) -> Tuple[List[int], dict]:

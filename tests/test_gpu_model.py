@@ -80,6 +80,9 @@ def test_greedy_decode_graph_equals_eager_and_reference(cuda_device, tmp_path, n
     e_toks, _ = utils.generate_tokens(model, prompt, max_tokens=48, use_cuda_graph=False)
     assert len(g_toks) == 48 and stats["generation_tps"] > 0
     assert g_toks == e_toks  # the graph replays exactly the eager computation
+    # the sampler inside the captured step (no host round trip per token) yields the same tokens
+    d_toks, d_stats = utils.generate_tokens_device(model, prompt, max_tokens=48)
+    assert d_toks == g_toks and d_stats["generation_tps"] > 0
     # chunked prefill (utils.py:312-319 semantics) does not change the tokens
     c_toks, _ = utils.generate_tokens(model, prompt, max_tokens=16, prefill_step_size=5)
     assert c_toks == g_toks[:16]
@@ -92,3 +95,14 @@ def test_greedy_decode_graph_equals_eager_and_reference(cuda_device, tmp_path, n
     clear = (top2[:, 0] - top2[:, 1]) > 0.05 * ref.abs().max()
     assert clear.sum() >= 24, f"only {int(clear.sum())} decisive steps"
     assert (ref.argmax(-1)[clear] == torch.tensor(g_toks)[clear]).all()
+
+
+def test_fast_argmax_is_torch_argmax(cuda_device):
+    """Two-stage vocabulary argmax of the device-side sampler: first occurrence on ties, any vocabulary size."""
+    g = torch.Generator(device=cuda_device).manual_seed(0)
+    for v in (128256, 152064, 512, 1000, 32000):
+        x = torch.randn((3, v), generator=g, device=cuda_device).to(torch.bfloat16)  # bf16: ties for the maximum do occur
+        x[1, 7] = x[1, v - 5] = x[1].max() + 1  # forced tie far apart
+        x[2, v - 1] = 100.0
+        assert torch.equal(utils.fast_argmax(x), torch.argmax(x, dim=-1)), v
+        assert torch.equal(utils.fast_argmax(x.float()), torch.argmax(x.float(), dim=-1)), v

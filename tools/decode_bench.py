@@ -53,6 +53,26 @@ def main():
         assert toks == toks0, "greedy decode is not reproducible run to run"
         if best is None or stats["generation_tps"] > best["generation_tps"]:
             best = stats
+    d_toks, d_stats = utils.generate_tokens_device(model, prompt, max_tokens=args.tokens)
+    d_toks, d_stats = utils.generate_tokens_device(model, prompt, max_tokens=args.tokens)
+    assert d_toks == toks0, "device-side greedy sampler diverged from the host-side one"
+    # device time of the captured decode step alone (no sampling, no host sync between steps)
+    from gbx_lm_b200 import qllama
+
+    cache = qllama.make_prompt_cache(model, 1, args.prompt + args.tokens + 1)
+    with torch.no_grad():
+        model(prompt[None].cuda(), cache)
+    dg = utils.DecodeGraph(model, cache).capture(torch.tensor([1], device="cuda"), args.prompt)
+    for _ in range(5):
+        dg.graph.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(50):
+        dg.graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    graph_ms = e0.elapsed_time(e1) / 50
     plan = W.layer_plan(dims, strat, 4, 64)
     body = sum(W.qmm_bytes(1, n, k, b, g) for (_, _, n, k, b, g) in plan)
     head = dims.vocab * dims.hidden * 2
@@ -60,6 +80,7 @@ def main():
         "tool": "decode_bench", "model": args.model, "strategy": args.strategy, "batch": 1, "prompt_tokens": args.prompt,
         "generation_tokens": best["generation_tokens"], "generation_tps": round(best["generation_tps"], 1),
         "prompt_tps": round(best["prompt_tps"], 1), "ms_per_token": round(1e3 / best["generation_tps"], 4),
+        "generation_tps_device_sampler": round(d_stats["generation_tps"], 1), "graph_ms_per_step": round(graph_ms, 4), "gbxq_launches_per_generate": best["gbxq_launches"],
         "qmm_bytes_per_token": body, "head_bytes_per_token": head,
         "hbm_gbs_body_plus_head": round((body + head) * best["generation_tps"] / 1e9, 1),
         "checkpoint_write_s": round(t_write, 1), "load_s": round(t_load, 1), "data": "synthetic (random-init, seed 0)",
