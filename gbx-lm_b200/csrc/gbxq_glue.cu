@@ -60,67 +60,76 @@ __global__ void rope_cache_kernel(__nv_bfloat16* __restrict__ q, const __nv_bflo
     }
 }
 
-// grid (Hq, B), block 128 threads (4 warps).  Warp w walks keys w, w+4, ... <= pos with an online softmax; lane l holds
-// elements l, l+32, ... of the head dimension.  The four partial states meet in shared memory.
-template <int DPL>  // head-dim elements per lane: D = 32 * DPL
-__global__ void __launch_bounds__(128) decode_attention_kernel(const __nv_bfloat16* __restrict__ q,
+// grid (Hq, B), block 256 threads, dynamic shared memory = one float per visible key.
+// Phase 1: one THREAD per key (keys tid, tid + 256, ...): the 16-byte loads of a key row are independent, so a block
+// has thousands of bytes in flight instead of one dependent load per warp and key (the first version of this kernel
+// walked the keys with an online softmax per warp and was latency-bound: +0.5 ms per 8B token at 100 keys).  Block max /
+// sum, probabilities back to shared memory.  Phase 2: thread = (key split, head-dim element), coalesced V rows.
+template <int D>
+__global__ void __launch_bounds__(256) decode_attention_kernel(const __nv_bfloat16* __restrict__ q,
                                                                const __nv_bfloat16* __restrict__ kc,
                                                                const __nv_bfloat16* __restrict__ vc,
                                                                const int64_t* __restrict__ pos_p,
                                                                __nv_bfloat16* __restrict__ out, int Hq, int Hkv,
                                                                int64_t max_len, int64_t attend_len, float scale) {
-    constexpr int D = 32 * DPL;
-    const int h = blockIdx.x, b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int SPLITS = 256 / D;
+    extern __shared__ float sc[];
+    __shared__ float qs[D], red[8], part[SPLITS][D];
+    const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int hk = h / (Hq / Hkv);
     pdl_wait_then_trigger();
     int64_t last = *pos_p;  // keys 0 .. pos are visible
     if (last >= attend_len) last = attend_len - 1;
-    const __nv_bfloat16* qp = q + ((size_t)b * Hq + h) * D;
+    const int n = (int)(last + 1);
     const __nv_bfloat16* kp = kc + ((size_t)b * Hkv + hk) * max_len * D;
     const __nv_bfloat16* vp = vc + ((size_t)b * Hkv + hk) * max_len * D;
-    float qv[DPL], acc[DPL];
-#pragma unroll
-    for (int e = 0; e < DPL; e++) {
-        qv[e] = bf(qp[lane + 32 * e]) * scale;
-        acc[e] = 0.f;
-    }
-    float m = -INFINITY, l = 0.f;
-    for (int64_t j = warp; j <= last; j += 4) {
+    if (tid < D) qs[tid] = bf(q[((size_t)b * Hq + h) * D + tid]) * scale;
+    __syncthreads();
+    float lmax = -INFINITY;
+    for (int j = tid; j < n; j += 256) {
+        const uint4* kr = reinterpret_cast<const uint4*>(kp + (size_t)j * D);
         float s = 0.f;
 #pragma unroll
-        for (int e = 0; e < DPL; e++) s = fmaf(qv[e], bf(kp[j * D + lane + 32 * e]), s);
-        s = warp_sum(s);
-        const float mn = fmaxf(m, s);
-        const float corr = __expf(m - mn), p = __expf(s - mn);
-        l = l * corr + p;
+        for (int v = 0; v < D / 8; v++) {
+            const uint4 u = kr[v];
+            const __nv_bfloat16* uv = reinterpret_cast<const __nv_bfloat16*>(&u);
 #pragma unroll
-        for (int e = 0; e < DPL; e++) acc[e] = fmaf(p, bf(vp[j * D + lane + 32 * e]), acc[e] * corr);
-        m = mn;
-    }
-    __shared__ float sm_m[4], sm_l[4], sm_acc[4][D];
-    if (lane == 0) {
-        sm_m[warp] = m;
-        sm_l[warp] = l;
+            for (int e = 0; e < 8; e++) s = fmaf(qs[8 * v + e], bf(uv[e]), s);
+        }
+        sc[j] = s;
+        lmax = fmaxf(lmax, s);
     }
 #pragma unroll
-    for (int e = 0; e < DPL; e++) sm_acc[warp][lane + 32 * e] = acc[e];
+    for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    if (lane == 0) red[warp] = lmax;
     __syncthreads();
-    if (warp == 0) {
-        float mm = fmaxf(fmaxf(sm_m[0], sm_m[1]), fmaxf(sm_m[2], sm_m[3]));
-        float ll = 0.f, w4[4];
+    float m = red[0];
 #pragma unroll
-        for (int w = 0; w < 4; w++) {
-            w4[w] = sm_m[w] == -INFINITY ? 0.f : __expf(sm_m[w] - mm);
-            ll += sm_l[w] * w4[w];
-        }
-        const float inv = ll > 0.f ? 1.f / ll : 0.f;
+    for (int w = 1; w < 8; w++) m = fmaxf(m, red[w]);
+    __syncthreads();
+    float lsum = 0.f;
+    for (int j = tid; j < n; j += 256) {
+        const float p = __expf(sc[j] - m);
+        sc[j] = p;
+        lsum += p;
+    }
+    lsum = warp_sum(lsum);
+    if (lane == 0) red[warp] = lsum;
+    __syncthreads();
+    float l = 0.f;
 #pragma unroll
-        for (int e = 0; e < DPL; e++) {
-            float o = 0.f;
+    for (int w = 0; w < 8; w++) l += red[w];
+    const int split = tid / D, d = tid % D;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int j = split; j < n; j += SPLITS) acc = fmaf(sc[j], bf(vp[(size_t)j * D + d]), acc);
+    part[split][d] = acc;
+    __syncthreads();
+    if (tid < D) {
+        float o = 0.f;
 #pragma unroll
-            for (int w = 0; w < 4; w++) o = fmaf(sm_acc[w][lane + 32 * e], w4[w], o);
-            out[((size_t)b * Hq + h) * D + lane + 32 * e] = tobf(o * inv);
-        }
+        for (int sp = 0; sp < SPLITS; sp++) o += part[sp][tid];
+        out[((size_t)b * Hq + h) * D + tid] = tobf(n > 0 && l > 0.f ? o / l : 0.f);
     }
 }
 
@@ -225,10 +234,30 @@ int launch_decode_attention(const void* q, const void* kc, const void* vc, const
     auto K = reinterpret_cast<const __nv_bfloat16*>(kc);
     auto V = reinterpret_cast<const __nv_bfloat16*>(vc);
     auto O = reinterpret_cast<__nv_bfloat16*>(out);
+    if (attend_len > 49152) return GBXQ_EUNSUPPORTED;  // one float of shared memory per visible key
+    const size_t smem = (size_t)attend_len * sizeof(float);
+    static bool configured = false;  // benign race: the attribute set is idempotent
+    if (!configured) {
+        cudaError_t ea = cudaFuncSetAttribute(decode_attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 49152 * 4);
+        if (ea == cudaSuccess)
+            ea = cudaFuncSetAttribute(decode_attention_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 49152 * 4);
+        if (ea != cudaSuccess) return check_cuda(ea);
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = mmv_get_pdl_mode() > 0 ? 1 : 0;
     cudaError_t e;
     switch (D) {
-        case 64: e = launch_pdl(decode_attention_kernel<2>, grid, dim3(128), st, Q, K, V, pos, O, Hq, Hkv, max_len, attend_len, scale); break;
-        case 128: e = launch_pdl(decode_attention_kernel<4>, grid, dim3(128), st, Q, K, V, pos, O, Hq, Hkv, max_len, attend_len, scale); break;
+        case 64: e = cudaLaunchKernelEx(&cfg, decode_attention_kernel<64>, Q, K, V, pos, O, Hq, Hkv, max_len, attend_len, scale); break;
+        case 128: e = cudaLaunchKernelEx(&cfg, decode_attention_kernel<128>, Q, K, V, pos, O, Hq, Hkv, max_len, attend_len, scale); break;
         default: return GBXQ_EUNSUPPORTED;
     }
     count_launch();

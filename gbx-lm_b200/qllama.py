@@ -161,7 +161,7 @@ class Attention(nn.Module):  # gbx_lm/models/qllama.py:39-96
         B, L, _ = x.shape
         # one grouped launch for the three projections of x (ref qllama.py:76 calls them back to back)
         q, k, v = ops.quantized_matmul_grouped(x, (self.q_proj, self.k_proj, self.v_proj))
-        if fused_decode_ok(x, L, cache) and self.head_dim in (64, 128):
+        if fused_decode_ok(x, L, cache) and self.head_dim in (64, 128) and cache.max_len <= 49152:
             # decode step: RoPE + cache write in one launch, one-query attention in another
             qh = q.view(B, self.n_heads, self.head_dim)
             ops.rope_cache(qh, k.view(B, self.n_kv_heads, self.head_dim), v.view(B, self.n_kv_heads, self.head_dim),

@@ -1,6 +1,6 @@
 #!/bin/bash
 # r01q: final state of the round: all GPU tests, smoke, default bench, end-to-end decode with the PDL-aware glue.
-TAG=${1:-r01q}
+TAG=${1:-r01t}
 O=gpurun_out
 mkdir -p $O
 timeout 600 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> $O/${TAG}_pytest.log; tail -4 $O/${TAG}_pytest.log
