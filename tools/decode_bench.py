@@ -84,7 +84,7 @@ def main():
         "qmm_bytes_per_token": body, "head_bytes_per_token": head,
         "hbm_gbs_body_plus_head": round((body + head) * best["generation_tps"] / 1e9, 1),
         "checkpoint_write_s": round(t_write, 1), "load_s": round(t_load, 1), "data": "synthetic (random-init, seed 0)",
-        "note": "whole decode step incl. torch glue (RMSNorm, RoPE, SDPA, bf16 head via cuBLAS) and one host sync per token",
+        "note": "whole decode step: quantized forwards + decode glue through libgbxq (GBXQ_FUSED_DECODE=0: torch glue), bf16 head via cuBLAS; generation_tps syncs with the host every token, generation_tps_device_sampler does not",
     }), flush=True)
 
 
