@@ -17,8 +17,13 @@
 //     CTA), which gives exactly the semantics of issuing the calls one after another on a stream;
 //   * the per-call maths is the unchanged mmv8 body (gbxq_mmv8_body.cuh, STREAM = true): results are bitwise equal
 //     to gbxq_qmm / gbxq_qmm_grouped.
+//   * call descriptors travel to shared memory by bulk copies issued two (consumers) / three (producer) calls ahead.
 // Deadlock safety: the launch is refused unless the occupancy query says the whole grid is co-resident, and every
 // spin has a 2 s globaltimer bail-out that flags the error instead of hanging the device.
+// Measured (profiles/r01h_stream_timeline.txt): the hand-over between two calls (counter, wait, x,
+// fragments, epilogue) costs ~4.2 us, as much as a dependent launch, and the consumers cannot drain a full ring faster
+// than HBM fills it, so the chain runs the 8B step at 0.43 of the HBM roofline against 0.45 for launch-per-call: it is
+// an API and `bench.py --stream 1`, not the default path, until the consumer loop is faster than the stream.
 #include <cstring>
 #include <vector>
 
