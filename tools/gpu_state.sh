@@ -1,21 +1,17 @@
 #!/bin/bash
-# Recover the measured state: full GPU tests, per-kernel M=1 sweeps, bench with both strategies.
-TAG=${1:-r01b}
+# Re-measure the state of the repo in ONE gpurun call (~6 GPU-minutes): tests, smoke, default bench, variants, the two
+# timelines, asymptotic rates, end-to-end decode.  Usage: gpurun --timeout 900 -- 'bash tools/gpu_state.sh r02a'
+TAG=${1:-state}
 O=gpurun_out
 mkdir -p $O
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/${TAG}_smi.txt 2>&1
-timeout 1500 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> $O/${TAG}_pytest.log
-tail -5 $O/${TAG}_pytest.log
-for k in gemv mmv mmv8; do
-  echo "== $k"; timeout 300 python tools/microbench.py --quick --kernel $k --ms 1,4 2>&1
-done > $O/${TAG}_micro_kernels.txt
-cat $O/${TAG}_micro_kernels.txt
-timeout 300 python tools/microbench.py --quick --kernel mmv8 --ms 1 --shapes big > $O/${TAG}_big.txt 2>&1; cat $O/${TAG}_big.txt
-timeout 600 python bench.py --steps 20 --warmup 5 > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err
-cat $O/${TAG}_bench.json; tail -3 $O/${TAG}_bench.err
-timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --pdl 0 > $O/${TAG}_bench_nopdl.json 2>> $O/${TAG}_bench.err
-cat $O/${TAG}_bench_nopdl.json
-timeout 600 python bench.py --steps 20 --warmup 5 --strategy bpw-2.2 --no-cpu-baseline > $O/${TAG}_bench_bpw22.json 2>> $O/${TAG}_bench.err
-cat $O/${TAG}_bench_bpw22.json
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:mmv8 -s 2 -c 1 -f -o $O/${TAG}_mmv8 python tools/ncu_one.py 14336 4096 4 64 1 mmv8 6 > $O/${TAG}_ncu.log 2>&1
-tail -2 $O/${TAG}_ncu.log
+timeout 300 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> $O/${TAG}_pytest.log; tail -3 $O/${TAG}_pytest.log
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.log 2>&1; tail -1 $O/${TAG}_smoke.log
+timeout 200 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; cat $O/${TAG}_bench.json
+b() { python -c "import json,sys; d=json.loads(sys.stdin.read()); print('bench', d['value'], d['ms_per_step'], d['roofline']['frac'], d['gpu_launches'], d['e2e']['value'])"; }
+for v in "--stream 1" "--strategy bpw-2.2" "--batch 2" "--batch 4" "--batch 16" "--model llama-3-70b --steps 5"; do
+  echo "== $v"; timeout 200 python bench.py --no-cpu-baseline $v 2>&1 | tail -1 | b
+done > $O/${TAG}_bench_variants.txt 2>&1; cat $O/${TAG}_bench_variants.txt
+for shp in "14336 4096 4 64" "4096 14336 4 64"; do echo "== timeline $shp"; timeout 100 python tools/timeline.py $shp 8 2; done > $O/${TAG}_timeline.txt 2>&1
+timeout 150 python tools/stream_timeline.py 8 > $O/${TAG}_stream_timeline.txt 2>&1; tail -7 $O/${TAG}_stream_timeline.txt
+for k in mmv8 skinny; do echo "== $k big"; timeout 120 python tools/microbench.py --quick --kernel $k --ms $([ $k = mmv8 ] && echo 1 || echo 8) --shapes big 2>&1 | grep -v "^shape"; done > $O/${TAG}_big.txt 2>&1; cat $O/${TAG}_big.txt
+timeout 150 python tools/decode_bench.py --model llama-3.2-1b --repeat 2 > $O/${TAG}_decode_1b.json 2> $O/${TAG}_decode_1b.err; cat $O/${TAG}_decode_1b.json
