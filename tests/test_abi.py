@@ -137,3 +137,62 @@ def test_quantized_linear_attribute_contract():
             assert (m.bias is not None) == (bits == 4)
             keys = set(m.state_dict().keys())
             assert {"qweight", "scales", "zeros", "channel_scale"} <= keys
+
+
+def test_stream_plan_blob_invariants():
+    """The descriptor blob gbxq_stream_plan writes (layout of StreamCallDev / Mmv8Params in gbxq_stream.cu and
+    gbxq_mmv8_body.cuh, restated here): every row of every projection belongs to exactly one CTA, stages are whole MMA
+    sets, a stage's weights, scales and biases fit the ring slot, and the ring fits the launch's shared memory."""
+    import struct
+
+    from gbx_lm_b200 import _lib
+
+    lib = _lib.get()
+    base = 1 << 20
+
+    def call(K, segs, dep=_lib.DEP_PREV):
+        c = _lib.StreamCall()
+        c.x, c.K, c.nseg, c.dep = base, K, len(segs), dep
+        for i, (bits, N, gs) in enumerate(segs):
+            c.segs[i] = _lib.Segment(base + 4096 * (i + 1), base, base, None, base, N, bits, gs)
+        return c
+
+    chains = {
+        1: [call(4096, [(4, 4096, 64), (2, 1024, 64), (8, 1024, 64)]), call(4096, [(4, 4096, 64)]),
+            call(4096, [(4, 14336, 64), (2, 14336, 64)]), call(14336, [(4, 4096, 64)], dep=1),
+            call(2048, [(4, 300, 64), (4, 1, 64)], dep=_lib.DEP_NONE), call(8192, [(2, 8192, 64)])],
+        2: [call(4096, [(4, 4096, 128), (4, 1024, 128)]), call(8192, [(8, 4096, 128)])],
+        4: [call(4096, [(4, 6144, 64)]), call(2048, [(2, 2048, 64), (4, 512, 64)])],
+    }
+    P, CALL = 136, 608  # sizeof(Mmv8Params), sizeof(StreamCallDev)
+    for M, calls in chains.items():
+        arr = (_lib.StreamCall * len(calls))(*calls)
+        info = _lib.StreamInfo()
+        assert lib.gbxq_stream_plan(arr, len(calls), M, 0, None, 0, ctypes.byref(info)) == 0
+        assert info.blob_bytes == CALL * len(calls) and info.mt == {1: 1, 2: 2, 4: 4}[M]
+        buf = ctypes.create_string_buffer(int(info.blob_bytes))
+        assert lib.gbxq_stream_plan(arr, len(calls), M, 0, buf, info.blob_bytes, ctypes.byref(info)) == 0
+        raw = buf.raw
+        for ci, c in enumerate(calls):
+            off = ci * CALL
+            cta0 = struct.unpack_from("5i", raw, off + 4 * P)
+            bits = struct.unpack_from("4i", raw, off + 4 * P + 20)
+            nseg, variant, dep = struct.unpack_from("3i", raw, off + 4 * P + 36)
+            assert nseg == c.nseg and 0 <= variant < 6
+            assert dep == (ci - 1 if c.dep == _lib.DEP_PREV else c.dep) and dep < ci
+            assert cta0[0] == 0 and all(cta0[i] <= cta0[i + 1] for i in range(4)) and cta0[4] <= info.grid
+            assert cta0[nseg] == cta0[4]
+            for s in range(nseg):
+                po = off + s * P
+                xq, wq, sq, bq, biasq, yq, N, K = struct.unpack_from("6Q2q", raw, po)
+                Mv, G, row_bytes, nch, cw, rg, tr, stages, slot_bytes, sb_off, early = struct.unpack_from("2i2I4i2Ii", raw, po + 64)
+                rows_base, rows_rem, spr0, spr1 = struct.unpack_from("4i", raw, po + 120)
+                sg = c.segs[s]
+                grid_s = cta0[s + 1] - cta0[s]
+                assert (N, K, bits[s], Mv) == (sg.N, c.K, sg.bits, M) and wq == sg.qweight and xq == c.x
+                assert G == K // sg.group_size and row_bytes == K * sg.bits // 8 and nch * 4 == G
+                assert grid_s >= 1 and rows_base * grid_s + rows_rem == N and 0 <= rows_rem < grid_s  # every row once
+                assert 1 <= cw * rg <= 8 and tr % 4 == 0 and spr0 % 4 == 0 and spr1 % 4 == 0 and 0 < spr0 <= tr and spr1 <= tr
+                assert stages == info.stages and slot_bytes == info.slot_bytes and early == 1
+                assert tr * row_bytes <= sb_off and sb_off + 2 * tr * G * 2 <= slot_bytes
+        assert 4096 + info.stages * info.slot_bytes < info.smem_bytes <= 112 * 1024
