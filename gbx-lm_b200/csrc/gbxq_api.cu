@@ -82,6 +82,9 @@ uint64_t gbxq_launch_count(void) { return g_launches.load(std::memory_order_rela
 // to `buf_dev`: entry, after griddepcontrol.wait, after the prologue, first stage landed, main loop done, CTA barrier,
 // exit.  tools/timeline.py prints them.
 void gbxq_debug_timeline(unsigned long long* buf_dev, int launches) { mmv8_debug_timeline(buf_dev, launches); }
+void gbxq_debug_timeline_all(unsigned long long* buf_dev, int launches, int stride_ctas) {
+    mmv8_debug_timeline_all(buf_dev, launches, stride_ctas);
+}
 
 void gbxq_debug_stream_timeline(void* host_blob, int ncalls, unsigned long long* dbg_dev) {
     stream_debug_patch(host_blob, ncalls, dbg_dev);

@@ -168,6 +168,7 @@ bool mmv8_supported(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype
 int launch_mmv8(const void* x, const uint32_t* w, const void* s, const void* b, const void* bias, void* y, int64_t M,
                 int64_t N, int64_t K, int bits, int gs, cudaStream_t st);
 void mmv8_debug_timeline(unsigned long long* buf, int launches);
+void mmv8_debug_timeline_all(unsigned long long* buf, int launches, int stride_ctas);
 int launch_mmv8_grouped(const gbxq_segment* segs, int nseg, const void* x, int64_t M, int64_t K, cudaStream_t st);
 int stream_plan(const gbxq_stream_call* calls, int ncalls, int64_t M, int dtype, void* host_blob, size_t cap,
                 gbxq_stream_info* info);

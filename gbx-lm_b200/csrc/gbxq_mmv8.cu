@@ -95,11 +95,19 @@ int launch_mt(const Mmv8Params& p, const Plan& pl, cudaStream_t st) {
 
 unsigned long long* g_dbg = nullptr;
 int g_dbg_left = 0;
+int g_dbg_stride = 0;  // > 0: all-CTA timeline, CTAs per launch region
 }  // namespace
 
 void mmv8_debug_timeline(unsigned long long* buf, int launches) {
     g_dbg = buf;
     g_dbg_left = launches;
+    g_dbg_stride = 0;
+}
+// every CTA stamps: launch i writes 8 slots per CTA at buf + i * 8 * stride_ctas
+void mmv8_debug_timeline_all(unsigned long long* buf, int launches, int stride_ctas) {
+    g_dbg = buf;
+    g_dbg_left = launches;
+    g_dbg_stride = stride_ctas;
 }
 
 bool mmv8_supported(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype, const void* x, const void* w,
@@ -121,7 +129,8 @@ int launch_mmv8(const void* x, const uint32_t* w, const void* s, const void* b, 
     Mmv8Params p = make_params(pl, x, w, s, b, bias, y, M, N, K, bits, gs, mmv_get_pdl_mode() >= 2 ? 1 : 0);
     if (g_dbg != nullptr && g_dbg_left > 0) {
         p.dbg = g_dbg;
-        g_dbg += 8;
+        p.dbg_all = g_dbg_stride > 0 && pl.grid <= g_dbg_stride ? 1 : 0;
+        g_dbg += g_dbg_stride > 0 ? (size_t)8 * g_dbg_stride : 8;
         g_dbg_left--;
     }
     switch (bits * 1000 + gs) {

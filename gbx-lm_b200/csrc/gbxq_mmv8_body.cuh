@@ -29,9 +29,11 @@ __device__ __forceinline__ unsigned long long gtime() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-#define STAMP(i)                                                                   \
-    do {                                                                           \
-        if (p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[i] = gtime(); \
+// timeline stamps (development aid): CTA 0 only, or every CTA (dbg_all: 8 slots per CTA, slot 5 = %smid)
+#define STAMP(i)                                                                                   \
+    do {                                                                                           \
+        if (p.dbg != nullptr && threadIdx.x == 0 && (p.dbg_all != 0 || blockIdx.x == 0))           \
+            p.dbg[(p.dbg_all != 0 ? (size_t)blockIdx.x * 8 : 0) + (i)] = gtime();                  \
     } while (0)
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -103,6 +105,7 @@ struct Mmv8Params {
     uint32_t sb_off;      // offset of the scales inside a slot (biases follow at sb_off + tr*G*2)
     int early_weights;    // 1: weights are immutable while the call is in flight -> stream them before griddepcontrol.wait
     unsigned long long* dbg;  // optional timeline (gbxq_debug_timeline): 8 globaltimer stamps per launch, CTA 0 / warp 0
+    int dbg_all;              // 1: every CTA stamps (8 slots per CTA)
     int rows_base, rows_rem;  // CTA b owns rows_base + (b < rows_rem) rows starting at b*rows_base + min(b, rows_rem)
     int spr0, spr1;           // rows per stage for CTAs with rows_base / rows_base+1 rows (balanced, whole MMA sets)
 };
@@ -223,14 +226,21 @@ __device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, ui
         const int cwi = warp % p.cw;  // chunk column
         const int rgi = warp / p.cw;  // row group
         const int g = lane >> 2, t = lane & 3;
-        // lane -> (weight row inside the set, group slice) of the two A-row parts (MMA rows g and g+8)
+        // lane -> (weight row inside the set, group slice) of the two A-row parts (MMA rows g and g+8).  The slices are
+        // rotated with the weight row so that the 16 lanes of one LDS.64 wavefront read ONE contiguous 128-byte piece:
+        // rows 2i / 2i+1 of a set take slices {0,1} / {2,3} for part A and the other pair for part B.  Rows of a stage are
+        // row_bytes apart (a multiple of 128: the same banks); with slices {0,1} for every row the two rows of a wavefront
+        // collided (r01i ncu: 4.3 wavefronts per useful one).  4-byte chunks (2-bit, gs 64) stay 2-way conflicting: a
+        // chunk column of theirs is only 64 bytes wide.
         const int wrow = g >> 1;
-        const int sA = g & 1, sB = 2 + (g & 1);
+        const int sA = g & 3;
+        const int sB = sA ^ 2;
         // lane as B-column holder: column g = (slice g>>1, digit g&1)
         const int bsl = g >> 1, bdig = g & 1;
         // accumulators c0,c1 (c2,c3) = columns 2t, 2t+1 = (slice t, digits 0/1): meaningful for part A iff t == sA,
         // for part B iff t == sB; this lane's meaningful part (if any) multiplies group slice t
-        const bool mean = (t & 1) == (g & 1);
+        const bool mean = ((t ^ sA) & 1) == 0;
+        const bool partA = t == sA;
 
         if constexpr (!STREAM) griddep_wait();  // x (and y) belong to the previous kernels of the stream
         STAMP(1);
@@ -396,7 +406,7 @@ __device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, ui
                 }
 #pragma unroll
                 for (int m = 0; m < MT; m++) {
-                    const int tt = (t & 2) ? T[m][1] : T[m][0];  // the part whose slice is t (garbage where !mean: dropped below)
+                    const int tt = partA ? T[m][0] : T[m][1];  // the part whose slice is t (garbage where !mean: dropped below)
                     yacc[q][m] = fmaf(sc * pw[m][j], (float)tt, yacc[q][m]);
                 }
             };
@@ -477,17 +487,35 @@ __device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, ui
     } else {
         __syncthreads();
         STAMP(5);
+        if (p.dbg != nullptr && p.dbg_all != 0 && threadIdx.x == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            p.dbg[(size_t)blockIdx.x * 8 + 5] = smid;
+        }
         griddep_wait();  // every thread stores y below (returns at once when a consumer warp has already waited)
     }
-    // ---- epilogue: one rounding to bf16, optional bias as a second rounded add, coalesced store
-    for (int i = threadIdx.x; i < rows * MT; i += (STREAM ? kCW * 32 : kThreads)) {
-        const int m = i / rows, r = i - m * rows;
-        if (m < p.M) {
-            float tot = 0.f;
-            for (int c = 0; c < slots; c++) tot += ysum[(r * slots + c) * MT + m];
-            float v = __bfloat162float(__float2bfloat16_rn(tot));
-            if (p.bias != nullptr) v = __fadd_rn(v, __bfloat162float(p.bias[r0 + r]));
-            p.y[(size_t)m * p.N + r0 + r] = __float2bfloat16_rn(v);
+    // ---- epilogue: 4 lanes per output row sum a quarter of the partial slots each (fixed order: deterministic), two
+    // shuffles, one rounding to bf16, optional bias as a second rounded add
+    {
+        constexpr int kNT = STREAM ? kCW * 32 : kThreads;
+        const int q4 = threadIdx.x & 3;
+#pragma unroll
+        for (int m = 0; m < MT; m++) {
+            for (int rb = 0; rb < rows; rb += kNT / 4) {  // trip count uniform over the CTA: full-mask shuffles
+                const int r = rb + ((int)threadIdx.x >> 2);
+                float tot = 0.f;
+                if (r < rows) {
+                    const float* src = ysum + ((size_t)r * slots) * MT + m;
+                    for (int c = q4; c < slots; c += 4) tot += src[c * MT];
+                }
+                tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+                tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+                if (q4 == 0 && r < rows && m < p.M) {
+                    float v = __bfloat162float(__float2bfloat16_rn(tot));
+                    if (p.bias != nullptr) v = __fadd_rn(v, __bfloat162float(p.bias[r0 + r]));
+                    p.y[(size_t)m * p.N + r0 + r] = __float2bfloat16_rn(v);
+                }
+            }
         }
     }
     STAMP(6);
@@ -545,7 +573,8 @@ inline Plan make_plan(int64_t M, int64_t N, int64_t K, int bits, int gs, int gri
     const uint32_t wpart = (uint32_t)(((int64_t)pl.tr * row_bytes + 127) & ~(int64_t)127);
     pl.sb_off = wpart;
     pl.slot_bytes = wpart + (uint32_t)((2 * (int64_t)pl.tr * G * 2 + 127) & ~(int64_t)127);
-    pl.stages = kPlanStages;
+    static const int plan_stages = env_int("GBXQ_MMV8_STAGES", kPlanStages);
+    pl.stages = plan_stages < 2 ? 2 : (plan_stages > kMaxStages ? kMaxStages : plan_stages);
     while (pl.stages > 2 && (size_t)pl.stages * pl.slot_bytes > (size_t)ring_kb * 1024) pl.stages--;
     int grid = grid_want > 0 ? grid_want : device_sm_count() * grid_mult;
     const int64_t min_rows = pl.tr;

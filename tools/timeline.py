@@ -49,3 +49,48 @@ print(f"N={n} K={k} bits={bits} gs={gs} pdl={pdl}: ns relative to launch 0 entry
 for i in range(L):
     print(i, " ".join(f"{int(v - t0):7d}" for v in t[i, :7]), "  | dur", int(t[i, 6] - t[i, 0]), " wait->x", int(t[i, 7] - t[i, 1]),
           " exit->next waited", int(t[i + 1, 1] - t[i, 6]) if i + 1 < L else "")
+
+# ---- all-CTA timeline: where the hand-over between dependent launches goes (entry / waited / loop end / exit of EVERY
+# CTA of every launch; per launch the spread of each stamp over the grid and the gap to the next launch)
+if os.environ.get("TIMELINE_ALL", "1") != "0":
+    import numpy as np
+
+    lib.gbxq_debug_timeline_all.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    lib.gbxq_debug_timeline_all.restype = None
+    STRIDE = 2048
+    big = torch.zeros((L, STRIDE, 8), dtype=torch.int64, device=dev)
+    g2 = torch.cuda.CUDAGraph()
+    lib.gbxq_debug_timeline_all(big.data_ptr(), L, STRIDE)
+    with torch.cuda.graph(g2):
+        chain()
+    lib.gbxq_debug_timeline_all(0, 0, 0)
+    for _ in range(3):
+        g2.replay()
+    torch.cuda.synchronize()
+    a = big.cpu().numpy()
+    live = a[:, :, 0] != 0
+    base = a[0, :, 0][live[0]].min()
+    print("all CTAs: per launch, ns relative to the first entry of launch 0: min / median / max over the grid")
+    cols = {"entry": 0, "waited": 1, "prologue": 2, "stage0": 3, "loopend": 4, "exit": 6}
+    for i in range(L):
+        m = live[i]
+        n_cta = int(m.sum())
+        row = [f"L{i} ctas={n_cta}"]
+        for nm, c in cols.items():
+            v = a[i, m, c] - base
+            row.append(f"{nm} {int(v.min())}/{int(np.median(v))}/{int(v.max())}")
+        print("  ".join(row))
+        if i + 1 < L and live[i + 1].any():
+            nxt = a[i + 1, live[i + 1], 1] - base
+            ex = a[i, m, 6] - base
+            print(f"     last exit -> next waited(min) {int(nxt.min() - ex.max())} ns;  exit spread {int(ex.max() - ex.min())} ns;"
+                  f"  loop time min/med/max {int((a[i, m, 4] - a[i, m, 3]).min())}/{int(np.median(a[i, m, 4] - a[i, m, 3]))}/{int((a[i, m, 4] - a[i, m, 3]).max())}")
+    # exit time versus SM for one middle launch: are the stragglers whole SMs?
+    i = min(3, L - 1)
+    m = live[i]
+    sm = a[i, m, 5]
+    ex = a[i, m, 6] - base
+    en = a[i, m, 0] - base
+    order = np.argsort(ex)
+    print(f"launch {i}: 10 earliest exits (exit, entry, smid):", [(int(ex[j]), int(en[j]), int(sm[j])) for j in order[:10]])
+    print(f"launch {i}: 10 latest exits   (exit, entry, smid):", [(int(ex[j]), int(en[j]), int(sm[j])) for j in order[-10:]])
