@@ -106,6 +106,7 @@ struct Mmv8Params {
     int early_weights;    // 1: weights are immutable while the call is in flight -> stream them before griddepcontrol.wait
     unsigned long long* dbg;  // optional timeline (gbxq_debug_timeline): 8 globaltimer stamps per launch, CTA 0 / warp 0
     int dbg_all;              // 1: every CTA stamps (8 slots per CTA)
+    int pre_stages;           // > 0: the producer issues only this many stages until the activations have been read
     int rows_base, rows_rem;  // CTA b owns rows_base + (b < rows_rem) rows starting at b*rows_base + min(b, rows_rem)
     int spr0, spr1;           // rows per stage for CTAs with rows_base / rows_base+1 rows (balanced, whole MMA sets)
 };
@@ -169,6 +170,7 @@ __device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, ui
                 mbar_init(&full_bar[s], 1);
                 mbar_init(&empty_bar[s], active_warps);
             }
+            mbar_init(&full_bar[kMaxStages - 1], active_warps);  // "activations read" (plans use < kMaxStages stages)
             fence_mbar_init();
         }
         __syncthreads();
@@ -202,7 +204,11 @@ __device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, ui
             if (!p.early_weights) griddep_wait();
             const uint8_t* wsrc = p.w + (uint64_t)r0 * p.row_bytes;
             const uint32_t g2 = (uint32_t)p.G * 2u;
+            int issued = 0;
             for (int ra = 0; ra < rows; ra += spr) {
+                // hold the stream back while the consumers fetch the activations: with every SM's ring filling, a load
+                // that hits in L2 takes ~1 us instead of ~0.3 us (profiles/r02a_timeline_allcta.txt: waited -> x)
+                if (p.pre_stages > 0 && issued++ == p.pre_stages) mbar_wait(&full_bar[kMaxStages - 1], 0u);
                 mbar_wait(&empty_bar[s], phase ^ 1u);
                 int nr = rows - ra;
                 if (nr > spr) nr = spr;
@@ -338,6 +344,9 @@ __device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, ui
             }
         }
         __syncwarp();
+        if constexpr (!STREAM) {
+            if (lane == 0) mbar_arrive(&full_bar[kMaxStages - 1]);  // activations are in registers: the stream may flood
+        }
         const int brow = lane / LPR, bq = lane % LPR;
         const uint32_t g2 = (uint32_t)p.G * 2u;
         const int lrow0 = rgi * R;
@@ -574,7 +583,7 @@ inline Plan make_plan(int64_t M, int64_t N, int64_t K, int bits, int gs, int gri
     pl.sb_off = wpart;
     pl.slot_bytes = wpart + (uint32_t)((2 * (int64_t)pl.tr * G * 2 + 127) & ~(int64_t)127);
     static const int plan_stages = env_int("GBXQ_MMV8_STAGES", kPlanStages);
-    pl.stages = plan_stages < 2 ? 2 : (plan_stages > kMaxStages ? kMaxStages : plan_stages);
+    pl.stages = plan_stages < 2 ? 2 : (plan_stages > kMaxStages - 1 ? kMaxStages - 1 : plan_stages);
     while (pl.stages > 2 && (size_t)pl.stages * pl.slot_bytes > (size_t)ring_kb * 1024) pl.stages--;
     int grid = grid_want > 0 ? grid_want : device_sm_count() * grid_mult;
     const int64_t min_rows = pl.tr;
@@ -625,6 +634,8 @@ inline Mmv8Params make_params(const Plan& pl, const void* x, const uint32_t* w, 
     p.slot_bytes = pl.slot_bytes;
     p.sb_off = pl.sb_off;
     p.early_weights = early;
+    static const int pre_stages = env_int("GBXQ_MMV8_PRE_STAGES", 2);
+    p.pre_stages = pre_stages;
     p.rows_base = (int)(N / pl.grid);
     p.rows_rem = (int)(N % pl.grid);
     auto spr_of = [&](int rows) {

@@ -178,3 +178,108 @@ def test_quantize_roundtrip_error_bound():
         d = A.dequantize(qw, s, b, 64, bits, "f32")
         step = np.abs(np.repeat(s, 64, -1))
         assert (np.abs(d - w) <= 1.01 * step + 1e-6).all()  # edge-anchored scale: at most one step at the far end
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Pins that do not come from the code under test (round 2):
+#   * tests/golden/hf_metal_golden.json -- written by HuggingFace transformers' Metal/MLX affine-quantisation host code
+#     (tests/golden/make_hf_golden.py), a foreign producer of the layout mx.quantized_matmul reads (2/4/8-bit)
+#   * oracle/indep_check.py -- bit-by-bit, exact-rational evaluation of the documentation formulas (oracle/MLX_SPEC.md)
+# ---------------------------------------------------------------------------------------------------------------
+from fractions import Fraction  # noqa: E402
+
+from oracle import indep_check as I  # noqa: E402
+
+HF = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "hf_metal_golden.json")))
+
+
+@pytest.mark.parametrize("case", HF["cases"], ids=lambda c: f"hf-b{c['bits']}-g{c['group_size']}")
+def test_foreign_vectors_pin_packing_and_affine_map(case):
+    bits, gs, n, k = case["bits"], case["group_size"], case["N"], case["K"]
+    w = np.array(case["qweight"], dtype=np.uint32)
+    s = np.array(case["scales_f32_hex"], dtype=np.uint32).view(np.float32)
+    b = np.array(case["biases_f32_hex"], dtype=np.uint32).view(np.float32)
+    want = np.array(case["dequant_f32_hex"], dtype=np.uint32)
+    assert w.shape == (n, k * bits // 32)
+    # numpy oracle and C oracle reproduce the foreign dequantised matrix bit for bit (fp32)
+    d = A.dequantize(w, s, b, gs, bits, "f32")
+    assert (d.view(np.uint32) == want).all()
+    dc = C.dequantize(w, s, b, gs, bits, "f32")
+    assert (dc.view(np.uint32) == want).all()
+    # the ramp group of row 0 exercises every code: unpacked codes are monotone and span 0 .. 2^bits-1
+    q = A.unpack_codes(w, bits)
+    assert q[0, :gs].min() == 0 and q[0, :gs].max() == (1 << bits) - 1
+    assert (np.diff(q[0, :gs].astype(np.int32)) >= 0).all()
+    # the foreign fp64 matmul against the oracle's fp64 truth
+    x = np.array(case["x_f32_hex"], dtype=np.uint32).view(np.float32)
+    y = A.quantized_matmul(x, w, s, b, gs, bits, "f32", "f64")
+    np.testing.assert_allclose(y, np.array(case["y_f64"]), rtol=1e-5, atol=1e-6)
+    # independent bit-by-bit checker on two rows
+    for r in (0, n - 1):
+        sc = [Fraction(float(v)) for v in s[r]]
+        bi = [Fraction(float(v)) for v in b[r]]
+        row = I.dequantize_row(w[r], sc, bi, gs, bits, "f32", k)
+        assert [I.to_f32_bits(v) for v in row] == want[r].tolist()
+
+
+@pytest.mark.parametrize("bits", A.SUPPORTED_BITS)
+@pytest.mark.parametrize("dtype", ["bf16", "f16", "f32"])
+def test_three_independent_checkers_agree(bits, dtype):
+    """numpy oracle == C oracle == bit-by-bit rational checker: packing (incl. the straddling 3-/6-bit codes), the
+    two-rounding dequantize in every dtype, and the exact matmul."""
+    rng = np.random.default_rng(100 + bits)
+    gs, n, k = 32, 3, 96
+    q = rng.integers(0, 1 << bits, size=(n, k), dtype=np.uint8)
+    w = A.pack_codes(q, bits)
+    # independent packer: bit by bit
+    for r in range(n):
+        words = [0] * (k * bits // 32)
+        for kk in range(k):
+            I.put_code(words, kk, bits, int(q[r, kk]))
+        assert words == w[r].tolist()
+        assert [I.code_at(w[r], kk, bits) for kk in range(k)] == q[r].tolist()
+    sf = (rng.random((n, k // gs)).astype(np.float32) + 0.5) * np.float32(0.013)
+    bf = -(rng.random((n, k // gs)).astype(np.float32) + 0.5) * np.float32(0.4)
+    if dtype == "bf16":
+        s, b = A.f32_to_bf16_bits(sf), A.f32_to_bf16_bits(bf)
+        sbits, bbits = s, b
+    elif dtype == "f16":
+        s, b = sf.astype(np.float16), bf.astype(np.float16)
+        sbits, bbits = s.view(np.uint16), b.view(np.uint16)
+    else:
+        s, b = sf, bf
+        sbits, bbits = s.view(np.uint32), b.view(np.uint32)
+    d = A.dequantize(w, s, b, gs, bits, dtype).astype(np.float32)
+    cs = s if dtype == "f32" else np.ascontiguousarray(sbits).view(np.uint16)
+    cb = b if dtype == "f32" else np.ascontiguousarray(bbits).view(np.uint16)
+    dc = C.dequantize(w, cs, cb, gs, bits, dtype)
+    for r in range(n):
+        sc = [I.from_bits(int(v), dtype) for v in sbits[r]]
+        bi = [I.from_bits(int(v), dtype) for v in bbits[r]]
+        row = I.dequantize_row(w[r], sc, bi, gs, bits, dtype, k)
+        assert [I.to_f32_bits(v) for v in row] == d[r].view(np.uint32).tolist()
+        if dtype == "bf16":
+            assert [I.to_f32_bits(v) >> 16 for v in row] == dc[r].tolist()
+        # exact rational matmul of one x row against the oracle's fp64 truth
+        x = rng.standard_normal(k).astype(np.float32)
+        xq = A._round_to(x, dtype)
+        yt = A.quantized_matmul(xq if dtype != "bf16" else A.f32_to_bf16_bits(x), w[r:r + 1], s[r:r + 1], b[r:r + 1], gs, bits, dtype, "f64")
+        exact = I.qmm_row([Fraction(float(v)) for v in xq], w[r], sc, bi, gs, bits, k)
+        # the oracle returns the fp64 sum rounded once to the output dtype: equal to the exact sum rounded (or its
+        # neighbour when the fp64 sum sits within 1e-12 of a tie)
+        ulp = {"bf16": 2.0 ** -7, "f16": 2.0 ** -10, "f32": 2.0 ** -23}[dtype] * max(abs(float(exact)), 1e-3)
+        got = float(np.asarray(yt, dtype=np.float64).ravel()[0])
+        assert got == float(I.rne(exact, dtype)) or abs(got - float(exact)) <= ulp
+
+
+def test_indep_rne_matches_hardware_formats():
+    rng = np.random.default_rng(5)
+    v = rng.standard_normal(300).astype(np.float64) * 7.3
+    v[:3] = [1.0 + 2.0 ** -8, 1.0 + 3 * 2.0 ** -8, 2.0 ** -130]  # ties and a bf16/f32 subnormal
+    for val in v:
+        fr = Fraction(float(val))
+        assert float(I.rne(fr, "f32")) == float(np.float32(val))
+        assert float(I.rne(fr, "f16")) == float(np.float16(val)) or abs(val) < 6e-5
+        want = A.bf16_bits_to_f32(A.f32_to_bf16_bits(np.array([np.float32(val)])))[0]
+        # bf16 from the fp64 value directly vs via fp32: identical unless the fp32 step itself lands on a tie
+        assert float(I.rne(Fraction(float(np.float32(val))), "bf16")) == float(want)
