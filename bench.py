@@ -139,33 +139,63 @@ def run_gbxq(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    # row-parallel epilogue: one-shot NVLink all-reduce over peer memory (gbxq_allreduce_oneshot; 8 KB .. 1 MB decode
-    # messages are latency-bound) unless --allreduce nccl, or symmetric memory cannot be set up on this box
-    allreduce, ar_kind = None, "none"
+    # row-parallel layers under TP (--allreduce): "fused" = the all-reduce inside the matmul kernel
+    # (gbxq_qmm_rowpar_allreduce: P2P pushes of fp32 partials over NVLink, per-CTA flags, rank-order sum);
+    # "oneshot" = matmul, then the stand-alone peer-memory all-reduce kernel; "nccl" = matmul, then ncclAllReduce.
+    # Every choice is self-checked against NCCL before it is trusted; what actually ran is recorded in the line.
     from gbx_lm_b200 import workloads as _W
+    from gbx_lm_b200.tp import TPContext
 
     dims_hidden = _W.MODELS[args.model].hidden
+    tpctx, ar_kind = TPContext(), "none"
     if world > 1:
-        ar_kind = "nccl"
-        if args.allreduce == "oneshot":
+        ar_kind, oneshot, fused = "nccl", None, None
+        if args.allreduce in ("oneshot", "fused"):
             try:
                 from gbx_lm_b200.tp import OneShotAllReduce
 
-                allreduce = OneShotAllReduce(None, dev, capacity_elems=max(1 << 16, 4 * args.batch * 8192))
-                # self-check against NCCL on a random vector, twice (both staging halves), before trusting it
-                for i in range(2):
+                oneshot = OneShotAllReduce(None, dev, capacity_elems=max(1 << 16, 4 * args.batch * 8192))
+                for i in range(3):  # both staging halves and a wrap
                     t = torch.randn(args.batch * dims_hidden, generator=torch.Generator(device=dev).manual_seed(7 * rank + i), device=dev).to(torch.bfloat16)
                     want = t.float()
                     dist.all_reduce(want)
-                    got = allreduce(t.clone()).float()
+                    got = oneshot(t.clone()).float()
                     if not torch.allclose(got, want, rtol=2e-2, atol=2e-2):
                         raise RuntimeError("one-shot all-reduce self-check failed")
-                ar_kind = "gbxq_allreduce_oneshot (peer memory over NVLink)"
+                ar_kind = "gbxq_allreduce_oneshot (peer memory over NVLink, separate PDL launch)"
             except Exception as e:  # noqa: BLE001
-                allreduce = None
+                oneshot = None
                 ar_kind = f"nccl (one-shot unavailable: {type(e).__name__}: {str(e)[:80]})"
-        if allreduce is None:
-            allreduce = lambda t: dist.all_reduce(t)  # noqa: E731
+        if args.allreduce == "fused":
+            try:
+                from gbx_lm_b200.tp import FusedRowParallel
+
+                fused = FusedRowParallel(None, dev, max_elems=max(4 * 8192, args.batch * dims_hidden))
+                # self-check: a K-sharded layer through the fused kernel against matmul + NCCL sum of the same shards
+                gchk = torch.Generator(device=dev).manual_seed(99 + rank)
+                lin = QuantizedLinear(1024, dims_hidden, bias=False, group_size=64, bits=4)
+                lin._set("qweight", torch.randint(-(2 ** 31), 2 ** 31 - 1, (dims_hidden, 128), generator=gchk, device=dev, dtype=torch.int64).to(torch.int32).view(torch.uint32))
+                lin._set("scales", ((torch.rand((dims_hidden, 16), generator=gchk, device=dev) + 0.5) * 0.004).to(torch.bfloat16))
+                lin._set("zeros", (-lin.scales.float() * 7.5).to(torch.bfloat16))
+                lin._set("channel_scale", None)
+                for i in range(3):
+                    xx = torch.randn((min(args.batch, 4), 1024), generator=gchk, device=dev).to(torch.bfloat16)
+                    want = lin(xx).float()
+                    dist.all_reduce(want)
+                    got = fused(lin, xx)
+                    if got is None:
+                        raise RuntimeError("fused row-parallel kernel does not serve this batch")
+                    if not torch.allclose(got.float(), want, rtol=3e-2, atol=3e-2):
+                        raise RuntimeError("fused row-parallel self-check failed")
+                    chk = got.float().clone()
+                    dist.all_reduce(chk, op=dist.ReduceOp.MAX)
+                    if not torch.equal(chk, got.float()):
+                        raise RuntimeError("fused row-parallel result differs between ranks")
+                ar_kind = "fused into the row-parallel matmul kernel (gbxq_qmm_rowpar_allreduce: P2P fp32 pushes over NVLink, per-CTA flags)"
+            except Exception as e:  # noqa: BLE001
+                fused = None
+                ar_kind += f" [fused unavailable: {type(e).__name__}: {str(e)[:80]}]"
+        tpctx = TPContext(rank, world, None, oneshot, fused)
 
     ops.set_pdl_mode(args.pdl)
     dims, full_plan = build_plan(args)
@@ -173,11 +203,11 @@ def run_gbxq(args):
     # --parallelism: how N > 1 GPUs are used.  tp = tensor-parallel shards of ONE model instance (column-parallel
     # q/k/v/gate/up, row-parallel o/down + sum all-reduce; strong scaling) -- what the 32B / 70B configurations need;
     # dp = one full model replica per GPU, independent decode streams, no data-path collective (weak scaling) -- the
-    # deployment of a model that fits one GPU.  auto: dp for <= 8B, tp above.  At N > 1 the other mode is measured
-    # as well and reported under "also".
+    # deployment of a model that fits one GPU.  auto = tp (the headline at N > 1); the other mode is measured as well
+    # and reported under "also".
     mode = args.parallelism
     if mode == "auto":
-        mode = "tp" if args.model in ("qwen2.5-32b", "llama-3-70b") else "dp"
+        mode = "tp"  # north_star: N > 1 = tensor-parallel shards of ONE model with an all-reduce after o_proj / down_proj
     if world == 1:
         mode = "single"
 
@@ -241,15 +271,16 @@ def run_gbxq(args):
                 for ch, ar in chains:
                     ch.run()
                     if ar is not None:
-                        allreduce(ar)
+                        tpctx.all_reduce(ar)
                 outs[0] = stream_y
                 return
             y = None
             for p, ms in calls:
                 if len(ms) == 1:
-                    y = ms[0](xbuf[ms[0].input_dims])
                     if tp > 1 and p in ("o_proj", "down_proj"):
-                        allreduce(y)
+                        y = tpctx.row_parallel(ms[0], xbuf[ms[0].input_dims])
+                    else:
+                        y = ms[0](xbuf[ms[0].input_dims])
                 else:
                     y = ops.quantized_matmul_grouped(xbuf[ms[0].input_dims], ms)[0]
             outs[0] = y
@@ -341,6 +372,7 @@ def run_gbxq(args):
         rep2 = world if other == "dp" else 1
         b2 = sum(W.qmm_bytes(M, n, k, b, g) for (_, _, n, k, b, g) in full_plan) * rep2
         also = {"parallelism": f"{other}{world}", "scaling": "weak" if other == "dp" else "strong",
+                "allreduce": ar_kind if other == "tp" else "none (independent replicas)",
                 "value": round(b2 / (r2["ms_step"] * 1e-3) / 1e9, 2), "unit": UNIT, "ms_per_step": round(r2["ms_step"], 5),
                 "decode_tok_s_qmm_only": round(1e3 / r2["ms_step"] * M * rep2, 2)}
         del r2
@@ -430,7 +462,7 @@ def cpu_sample(args, layers_for_cpu=None, M=1, budget_s=12.0):
             L = A.synth_layer(n, k, b, g, seed=i * 7 + len(data))
             data.append((L["qweight"], L["scales"], L["zeros"], b, g))
     xs = {k: A.synth_x(M, k, seed=3) for k in {d[0].shape[1] * 32 // d[3] for d in data}}
-    threads = C.max_threads()
+    threads = max(C.max_threads(), int(os.environ.get("GBXQ_CPU_THREADS", "0")))  # explicit omp_set_num_threads in the C call
     nbytes = sum(W.qmm_bytes(M, d[0].shape[0], d[0].shape[1] * 32 // d[3], d[3], d[4]) for d in data)
 
     def one_pass():
@@ -456,6 +488,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; only rank 0 works here, on all host cores
+    os.environ["GBXQ_CPU_THREADS"] = str(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     from gbx_lm_b200 import workloads as W
 
     dims, plan = build_plan(args)
@@ -500,7 +534,7 @@ def main():
     ap.add_argument("--stream", type=int, default=0, help="1: the step's calls as one persistent chain launch (gbxq_qmm_stream); 0: one launch per call")
     ap.add_argument("--parallelism", default="auto", choices=["auto", "tp", "dp"], help="N > 1: tensor-parallel shards or independent replicas")
     ap.add_argument("--no-also", action="store_true", help="N > 1: skip the measurement of the other parallelism mode")
-    ap.add_argument("--allreduce", default="oneshot", choices=["oneshot", "nccl"], help="row-parallel epilogue under TP")
+    ap.add_argument("--allreduce", default="fused", choices=["fused", "oneshot", "nccl"], help="row-parallel layers under TP: all-reduce fused into the matmul kernel, stand-alone peer-memory kernel, or NCCL")
     ap.add_argument("--pdl", type=int, default=2, help="GBXQ_OPT_PDL (0 plain launches, 1 PDL, 2 PDL + early weight streaming)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -12,6 +12,7 @@ BF16, F16, F32 = 0, 1, 2
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_GEMV, KERNEL_GEMM, KERNEL_SKINNY, KERNEL_MMV, KERNEL_MMV8 = 0, 1, 2, 3, 4, 5, 6
 OPT_PDL = 1
 AR_MAX_CTAS = 32
+RP_MAX_CTAS = 512
 
 EXPORTS = (
     "gbxq_abi_version",
@@ -30,6 +31,7 @@ EXPORTS = (
     "gbxq_set_option",
     "gbxq_get_option",
     "gbxq_allreduce_oneshot",
+    "gbxq_qmm_rowpar_allreduce",
     "gbxq_rope_cache",
     "gbxq_decode_attention",
     "gbxq_add_rmsnorm",
@@ -50,6 +52,13 @@ class Segment(ctypes.Structure):
 
 
 DEP_PREV, DEP_NONE = -2, -1
+
+
+class Comm(ctypes.Structure):
+    """struct gbxq_comm (include/gbxq.h): peer staging buffers / flag arrays of a tensor-parallel group."""
+
+    _fields_ = [("peer_stage_host", ctypes.POINTER(ctypes.c_void_p)), ("peer_flags_host", ctypes.POINTER(ctypes.c_void_p)),
+                ("stage_elems", ctypes.c_int64), ("rank", ctypes.c_int), ("world", ctypes.c_int)]
 
 
 class StreamCall(ctypes.Structure):
@@ -133,6 +142,8 @@ def get() -> ctypes.CDLL:
     lib.gbxq_silu_mul.argtypes = [vp, vp, vp, i64, vp]
     lib.gbxq_allreduce_oneshot.restype = ci
     lib.gbxq_allreduce_oneshot.argtypes = [vp, vp, i64, ci, vp, vp, i64, ci, ci, u32, vp]
+    lib.gbxq_qmm_rowpar_allreduce.restype = ci
+    lib.gbxq_qmm_rowpar_allreduce.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, ci, ci, ci, ctypes.POINTER(Comm), vp]
     if lib.gbxq_abi_version() != 1:
         raise ImportError("libgbxq.so ABI version mismatch; rebuild with `python -m gbx_lm_b200.build --force`")
     _lib = lib

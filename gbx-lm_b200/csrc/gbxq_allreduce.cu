@@ -5,12 +5,17 @@
 // (symmetric memory).  Per call and per CTA slice:
 //   1. copy this rank's partial slice into its own staging half (seq parity)
 //   2. __threadfence_system(); publish `seq` into slot [rank][cta] of every peer's flag array
-//   3. spin until all peers have published `seq` for this slice
+//   3. spin until all peers have published `seq` for this slice (bounded: 4 s, then the error word
+//      [world*GBXQ_AR_MAX_CTAS + 2] of the own flag array is set and the call runs to its end)
 //   4. read the slice from every peer's staging half over NVLink, add in rank order in fp32,
 //      round once to T and store.
 // Rank-order summation makes the result bitwise identical on all ranks.  Double buffering by
 // seq parity is sufficient: a rank can only start call s after every peer signalled call s-1,
 // i.e. after every peer finished reading call s-2.
+// The launch carries the programmatic-dependent-launch attribute: it becomes resident while the matmul before it
+// drains (griddepcontrol.wait before the first read of `in`), and lets the kernel after it do the same.
+// For o_proj / down_proj at decode sizes the all-reduce inside the matmul kernel (gbxq_qmm_rowpar_allreduce,
+// gbxq_mmv8_body.cuh) replaces this kernel; it stays for the shapes that kernel does not serve.
 #include "gbxq_common.cuh"
 
 namespace gbxq {
@@ -27,7 +32,7 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 }
 
 template <typename T, int WORLD_MAX>
-__global__ void __launch_bounds__(256) allreduce_oneshot_kernel(const T* __restrict__ in, T* __restrict__ out,
+__global__ void __launch_bounds__(256) allreduce_oneshot_kernel(const T* in, T* out,  // may alias
                                                                 int64_t count, void* const* peer_bufs,
                                                                 uint32_t* const* peer_flags, int64_t half_elems,
                                                                 int rank, int world, uint32_t seq) {
@@ -41,6 +46,8 @@ __global__ void __launch_bounds__(256) allreduce_oneshot_kernel(const T* __restr
     // the CTAs that are done), so that a CUDA graph can replay the call: every CTA reads it at entry, the last CTA to
     // finish advances it.  The launch is plain stream-ordered, so the next call sees the advanced value.
     uint32_t* local = peer_flags[rank] + world * GBXQ_AR_MAX_CTAS;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // `in` (and the device-resident sequence number) belong to earlier kernels
     const bool dev_seq = seq == 0u;
     if (dev_seq) seq = *reinterpret_cast<volatile uint32_t*>(local) + 1u;
     const int64_t half = (int64_t)(seq & 1u) * half_elems;
@@ -56,7 +63,14 @@ __global__ void __launch_bounds__(256) allreduce_oneshot_kernel(const T* __restr
     // 3. wait for all peers (flags are monotonic: >= seq means published)
     if (threadIdx.x < world) {
         const uint32_t* f = peer_flags[rank] + threadIdx.x * GBXQ_AR_MAX_CTAS + blockIdx.x;
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         while ((int32_t)(ld_acquire_sys(f) - seq) < 0) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 4000000000ull) {  // a peer is gone or out of step: flag it, never hang the device
+                atomicExch(local + 2, 1u);
+                break;
+            }
         }
     }
     __syncthreads();
@@ -98,10 +112,20 @@ int launch_t(const void* in, void* out, int64_t count, void* const* peer_bufs, u
     int ctas = (int)((nvec + 255) / 256);
     if (ctas < 1) ctas = 1;
     if (ctas > GBXQ_AR_MAX_CTAS) ctas = GBXQ_AR_MAX_CTAS;
-    allreduce_oneshot_kernel<T, 8><<<ctas, 256, 0, st>>>((const T*)in, (T*)out, count, peer_bufs, peer_flags,
-                                                         capacity / 2, rank, world, seq);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)ctas);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = mmv_get_pdl_mode() > 0 ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, allreduce_oneshot_kernel<T, 8>, (const T*)in, (T*)out, count, peer_bufs,
+                                             peer_flags, capacity / 2, rank, world, seq);
     count_launch();
-    return check_cuda(cudaGetLastError());
+    return check_cuda(e);
 }
 
 }  // namespace

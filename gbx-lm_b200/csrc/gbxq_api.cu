@@ -156,6 +156,22 @@ int gbxq_qmm(const void* x, const uint32_t* qweight, const void* scales, const v
                        workspace, workspace_bytes, stream);
 }
 
+int gbxq_qmm_rowpar_allreduce(const void* x, const uint32_t* qweight, const void* scales, const void* biases,
+                              const void* bias, void* y, int64_t M, int64_t N, int64_t K, int bits, int group_size,
+                              int dtype, const gbxq_comm* comm, void* stream) {
+    const int rc = validate(M, N, K, bits, group_size, dtype);
+    if (rc != GBXQ_OK) return rc;
+    if (!comm || !comm->peer_stage_host || !comm->peer_flags_host) return GBXQ_ENULL;
+    if (comm->world < 1 || comm->world > 8 || comm->rank < 0 || comm->rank >= comm->world) return GBXQ_ESHAPE;
+    if (M == 0 || N == 0) return GBXQ_OK;
+    if (!x || !qweight || !scales || !biases || !y) return GBXQ_ENULL;
+    if (((uintptr_t)x | (uintptr_t)y | (uintptr_t)scales | (uintptr_t)biases | (uintptr_t)bias) & 1) return GBXQ_EALIGN;
+    if ((uintptr_t)qweight & 3) return GBXQ_EALIGN;
+    if (dtype != GBXQ_BF16 || M > 4 || !mmv8_supported(M, N, K, bits, group_size, dtype, x, qweight, y))
+        return GBXQ_EUNSUPPORTED;
+    return launch_mmv8_ar(x, qweight, scales, biases, bias, y, M, N, K, bits, group_size, comm, (cudaStream_t)stream);
+}
+
 int gbxq_qmm_grouped(const gbxq_segment* segs, int nseg, const void* x, int64_t M, int64_t K, int dtype, void* stream) {
     if (nseg < 0) return GBXQ_ESHAPE;
     if (nseg == 0) return GBXQ_OK;

@@ -10,6 +10,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/gbxq.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -29,6 +31,24 @@ inline int check_cuda(cudaError_t e) {
     }
     return GBXQ_OK;
 }
+
+// Per-DEVICE one-time configuration of a kernel (cudaFuncSetAttribute is a per-device property: a process that drives
+// several GPUs must set it on each).  `need()` is true until `done()` was called on the current device.
+struct DeviceOnce {
+    std::atomic<uint64_t> mask{0};
+    static int dev() {
+        int d = 0;
+        return (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < 64) ? d : -1;
+    }
+    bool need() const {
+        const int d = dev();
+        return d < 0 || !((mask.load(std::memory_order_relaxed) >> d) & 1u);
+    }
+    void done() {
+        const int d = dev();
+        if (d >= 0) mask.fetch_or(uint64_t(1) << d, std::memory_order_relaxed);
+    }
+};
 
 // ------------------------------------------------------------------ element types
 template <int DT> struct TypeOf;
@@ -167,6 +187,8 @@ bool mmv8_supported(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype
                     const void* y);
 int launch_mmv8(const void* x, const uint32_t* w, const void* s, const void* b, const void* bias, void* y, int64_t M,
                 int64_t N, int64_t K, int bits, int gs, cudaStream_t st);
+int launch_mmv8_ar(const void* x, const uint32_t* w, const void* s, const void* b, const void* bias, void* y, int64_t M,
+                   int64_t N, int64_t K, int bits, int gs, const gbxq_comm* comm, cudaStream_t st);
 void mmv8_debug_timeline(unsigned long long* buf, int launches);
 void mmv8_debug_timeline_all(unsigned long long* buf, int launches, int stride_ctas);
 int launch_mmv8_grouped(const gbxq_segment* segs, int nseg, const void* x, int64_t M, int64_t K, cudaStream_t st);

@@ -461,11 +461,11 @@ template <int BITS, int BN>
 int launch_inst(const Maps& mp, const GemmParams& p, cudaStream_t st) {
     constexpr size_t smem = Cfg<BITS, BN>::SMEM;
     static_assert(smem <= 227 * 1024, "shared memory budget");
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;  // per device: the attribute is a per-device property
+    if (configured.need()) {
         cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BITS, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return check_cuda(e);
-        configured = true;
+        configured.done();
     }
     dim3 grid((unsigned)((p.N + kTileN - 1) / kTileN), (unsigned)((p.M + BN - 1) / BN));
     gemm_kernel<BITS, BN><<<grid, kThreads, smem, st>>>(mp.x, mp.w, mp.s, mp.b, p);

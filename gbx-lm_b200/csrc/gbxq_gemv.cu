@@ -411,12 +411,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_kernel(const GemvParams p) {
 
 template <int BITS, int NSB, int MT, int CPW, bool SB_TMA>
 int launch_inst(const GemvParams& p, size_t smem_bytes, int grid, cudaStream_t st) {
-    static bool configured = false;  // benign race: attribute set is idempotent
-    if (!configured) {
+    static DeviceOnce configured;  // per device: the attribute is a per-device property
+    if (configured.need()) {
         cudaError_t e = cudaFuncSetAttribute(gemv_kernel<BITS, NSB, MT, CPW, SB_TMA>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return check_cuda(e);
-        configured = true;
+        configured.done();
     }
     gemv_kernel<BITS, NSB, MT, CPW, SB_TMA><<<grid, kThreads, smem_bytes, st>>>(p);
     count_launch();

@@ -236,13 +236,13 @@ int launch_decode_attention(const void* q, const void* kc, const void* vc, const
     auto O = reinterpret_cast<__nv_bfloat16*>(out);
     if (attend_len > 49152) return GBXQ_EUNSUPPORTED;  // one float of shared memory per visible key
     const size_t smem = (size_t)attend_len * sizeof(float);
-    static bool configured = false;  // benign race: the attribute set is idempotent
-    if (!configured) {
+    static DeviceOnce configured;  // per device: the attribute is a per-device property
+    if (configured.need()) {
         cudaError_t ea = cudaFuncSetAttribute(decode_attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 49152 * 4);
         if (ea == cudaSuccess)
             ea = cudaFuncSetAttribute(decode_attention_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 49152 * 4);
         if (ea != cudaSuccess) return check_cuda(ea);
-        configured = true;
+        configured.done();
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;

@@ -520,11 +520,11 @@ int g_pdl_mode = 2;  // 0: plain launches; 1: PDL, wait before any global read; 
 template <int BITS, int TB, int MP, int CPW, int R>
 int launch_inst(const MmvParams& p, const Plan& pl, cudaStream_t st) {
     auto kern = mmv_kernel<BITS, TB, MP, CPW, R>;
-    static bool configured = false;  // benign race: attribute set is idempotent
-    if (!configured) {
+    static DeviceOnce configured;  // per device: the attribute is a per-device property
+    if (configured.need()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
         if (e != cudaSuccess) return check_cuda(e);
-        configured = true;
+        configured.done();
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)pl.grid);

@@ -34,19 +34,19 @@ namespace {
 
 // BITS, GS = group size, MT = tokens (1, 2, 4), CPW = chunk columns per warp, R = rows per warp and stage (4 or 8)
 template <int BITS, int GS, int MT, int CPW, int R>
-__global__ void __launch_bounds__(kThreads, kMinCtas) mmv8_kernel(const Mmv8Params p) {
+__global__ void __launch_bounds__(kThreads, kMinCtas) mmv8_kernel(const Mmv8Params p, const __grid_constant__ ArParams ar) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    mmv8_body<BITS, GS, MT, CPW, R>(p, (int)blockIdx.x, smem);
+    mmv8_body<BITS, GS, MT, CPW, R>(p, (int)blockIdx.x, smem, nullptr, &ar);
 }
 
 template <int BITS, int GS, int MT, int CPW, int R>
-int launch_inst(const Mmv8Params& p, const Plan& pl, cudaStream_t st) {
+int launch_inst(const Mmv8Params& p, const ArParams& ar, const Plan& pl, cudaStream_t st) {
     auto kern = mmv8_kernel<BITS, GS, MT, CPW, R>;
-    static bool configured = false;  // benign race: attribute set is idempotent
-    if (!configured) {
+    static DeviceOnce configured;  // per device: the attribute is a per-device property
+    if (configured.need()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
         if (e != cudaSuccess) return check_cuda(e);
-        configured = true;
+        configured.done();
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)pl.grid);
@@ -58,25 +58,25 @@ int launch_inst(const Mmv8Params& p, const Plan& pl, cudaStream_t st) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = mmv_get_pdl_mode() > 0 ? 1 : 0;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p, ar);
     count_launch();
     return check_cuda(e);
 }
 
 template <int BITS, int GS, int MT>
-int launch_cpw(const Mmv8Params& p, const Plan& pl, cudaStream_t st) {
+int launch_cpw(const Mmv8Params& p, const ArParams& ar, const Plan& pl, cudaStream_t st) {
     if (pl.R == 8) {
-        if (pl.cpw == 1) return launch_inst<BITS, GS, MT, 1, 8>(p, pl, st);
-        if (pl.cpw == 2) return launch_inst<BITS, GS, MT, 2, 8>(p, pl, st);
+        if (pl.cpw == 1) return launch_inst<BITS, GS, MT, 1, 8>(p, ar, pl, st);
+        if (pl.cpw == 2) return launch_inst<BITS, GS, MT, 2, 8>(p, ar, pl, st);
     } else if (pl.R == 4) {
         switch (pl.cpw) {
-            case 1: return launch_inst<BITS, GS, MT, 1, 4>(p, pl, st);
-            case 2: return launch_inst<BITS, GS, MT, 2, 4>(p, pl, st);
+            case 1: return launch_inst<BITS, GS, MT, 1, 4>(p, ar, pl, st);
+            case 2: return launch_inst<BITS, GS, MT, 2, 4>(p, ar, pl, st);
             case 4:
-                if constexpr (MT <= 2) return launch_inst<BITS, GS, MT, 4, 4>(p, pl, st);
+                if constexpr (MT <= 2) return launch_inst<BITS, GS, MT, 4, 4>(p, ar, pl, st);
                 break;
             case 8:
-                if constexpr (MT == 1) return launch_inst<BITS, GS, MT, 8, 4>(p, pl, st);
+                if constexpr (MT == 1) return launch_inst<BITS, GS, MT, 8, 4>(p, ar, pl, st);
                 break;
         }
     }
@@ -84,11 +84,11 @@ int launch_cpw(const Mmv8Params& p, const Plan& pl, cudaStream_t st) {
 }
 
 template <int BITS, int GS>
-int launch_mt(const Mmv8Params& p, const Plan& pl, cudaStream_t st) {
+int launch_mt(const Mmv8Params& p, const ArParams& ar, const Plan& pl, cudaStream_t st) {
     switch (pl.mt) {
-        case 1: return launch_cpw<BITS, GS, 1>(p, pl, st);
-        case 2: return launch_cpw<BITS, GS, 2>(p, pl, st);
-        case 4: return launch_cpw<BITS, GS, 4>(p, pl, st);
+        case 1: return launch_cpw<BITS, GS, 1>(p, ar, pl, st);
+        case 2: return launch_cpw<BITS, GS, 2>(p, ar, pl, st);
+        case 4: return launch_cpw<BITS, GS, 4>(p, ar, pl, st);
     }
     return GBXQ_EUNSUPPORTED;
 }
@@ -123,10 +123,31 @@ bool mmv8_supported(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype
 
 int launch_mmv8(const void* x, const uint32_t* w, const void* s, const void* b, const void* bias, void* y, int64_t M,
                 int64_t N, int64_t K, int bits, int gs, cudaStream_t st) {
+    return launch_mmv8_ar(x, w, s, b, bias, y, M, N, K, bits, gs, nullptr, st);
+}
+
+// comm != nullptr: row-parallel shard with the all-reduce fused into the epilogue (gbxq_qmm_rowpar_allreduce)
+int launch_mmv8_ar(const void* x, const uint32_t* w, const void* s, const void* b, const void* bias, void* y, int64_t M,
+                   int64_t N, int64_t K, int bits, int gs, const gbxq_comm* comm, cudaStream_t st) {
     if (((uintptr_t)s | (uintptr_t)b) & 15) return GBXQ_EUNSUPPORTED;
     const Plan pl = make_plan(M, N, K, bits, gs);
-    if (!pl.ok) return GBXQ_EUNSUPPORTED;
+    if (!pl.ok || pl.cpw * pl.mt > 8) return GBXQ_EUNSUPPORTED;
     Mmv8Params p = make_params(pl, x, w, s, b, bias, y, M, N, K, bits, gs, mmv_get_pdl_mode() >= 2 ? 1 : 0);
+    ArParams ar{};
+    if (comm != nullptr && comm->world > 1) {
+        if (comm->world > 8 || comm->rank < 0 || comm->rank >= comm->world) return GBXQ_ESHAPE;
+        if (pl.grid > GBXQ_RP_MAX_CTAS) return GBXQ_EUNSUPPORTED;
+        if (comm->stage_elems < 2 * (int64_t)comm->world * M * N) return GBXQ_EWORKSPACE;
+        for (int r = 0; r < comm->world; r++) {
+            if (comm->peer_stage_host[r] == nullptr || comm->peer_flags_host[r] == nullptr) return GBXQ_ENULL;
+            if ((uintptr_t)comm->peer_stage_host[r] & 7) return GBXQ_EALIGN;
+            ar.stage[r] = reinterpret_cast<unsigned long long*>(comm->peer_stage_host[r]);
+            ar.flags[r] = comm->peer_flags_host[r];
+        }
+        ar.half_elems = comm->stage_elems / 2;
+        ar.world = comm->world;
+        ar.rank = comm->rank;
+    }
     if (g_dbg != nullptr && g_dbg_left > 0) {
         p.dbg = g_dbg;
         p.dbg_all = g_dbg_stride > 0 && pl.grid <= g_dbg_stride ? 1 : 0;
@@ -134,14 +155,14 @@ int launch_mmv8(const void* x, const uint32_t* w, const void* s, const void* b, 
         g_dbg_left--;
     }
     switch (bits * 1000 + gs) {
-        case 4064: return launch_mt<4, 64>(p, pl, st);
-        case 4128: return launch_mt<4, 128>(p, pl, st);
-        case 4032: return launch_mt<4, 32>(p, pl, st);
-        case 2064: return launch_mt<2, 64>(p, pl, st);
-        case 2128: return launch_mt<2, 128>(p, pl, st);
-        case 8064: return launch_mt<8, 64>(p, pl, st);
-        case 8128: return launch_mt<8, 128>(p, pl, st);
-        case 8032: return launch_mt<8, 32>(p, pl, st);
+        case 4064: return launch_mt<4, 64>(p, ar, pl, st);
+        case 4128: return launch_mt<4, 128>(p, ar, pl, st);
+        case 4032: return launch_mt<4, 32>(p, ar, pl, st);
+        case 2064: return launch_mt<2, 64>(p, ar, pl, st);
+        case 2128: return launch_mt<2, 128>(p, ar, pl, st);
+        case 8064: return launch_mt<8, 64>(p, ar, pl, st);
+        case 8128: return launch_mt<8, 128>(p, ar, pl, st);
+        case 8032: return launch_mt<8, 32>(p, ar, pl, st);
     }
     return GBXQ_EUNSUPPORTED;
 }

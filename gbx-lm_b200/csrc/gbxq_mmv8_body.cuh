@@ -11,6 +11,7 @@ constexpr int kCW = 8;                        // consumer warps
 constexpr int kThreads = (kCW + 1) * 32;      // + producer warp
 constexpr int kMaxStages = 8;                // barrier slots; one-call launches plan at most kPlanStages
 constexpr int kPlanStages = 4;
+constexpr int kArMaxCtas = GBXQ_RP_MAX_CTAS;
 #ifndef GBXQ_MMV8_MINCTAS
 #define GBXQ_MMV8_MINCTAS 2
 #endif
@@ -111,6 +112,19 @@ struct Mmv8Params {
     int spr0, spr1;           // rows per stage for CTAs with rows_base / rows_base+1 rows (balanced, whole MMA sets)
 };
 
+// Fused row-parallel all-reduce (world > 1, one-call launches only): every CTA pushes the fp32 partial sums of ITS rows
+// into every peer's staging buffer over NVLink and adds the `world` partials of its rows in rank order (bitwise identical
+// on all ranks).  Low-latency protocol: a partial travels as ONE 8-byte store {fp32 bits, epoch}; the receiver polls the
+// word itself until the epoch matches -- no fence, no separate flag, one NVLink one-way latency per exchange.
+// Staging of rank d: [2 halves (epoch parity)][world][M][N] 8-byte words, zeroed once; `flags` of the own rank: control
+// words {epoch, CTAs done, error} at [world * kArMaxCtas] (device-resident epoch: CUDA-graph replayable).
+struct ArParams {
+    unsigned long long* stage[8];
+    uint32_t* flags[8];
+    int64_t half_elems;
+    int world, rank;
+};
+
 // State a persistent chain launch (gbxq_stream.cu) carries from one call to the next: the ring position and the
 // device-wide completion counters that order the calls (x of a call may be the y of any earlier one).
 struct StreamCtx {
@@ -135,7 +149,9 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
 // STREAM = true: one call of a persistent chain, entered by the kCW consumer warps only; barriers (empty barriers
 // initialised to kCW arrivals) and the producer live in the caller, `sc` carries the ring position.
 template <int BITS, int GS, int MT, int CPW, int R, bool STREAM = false>
-__device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, uint8_t* smem, StreamCtx* sc = nullptr) {
+__device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, uint8_t* smem, StreamCtx* sc = nullptr,
+                                          const ArParams* ar = nullptr) {
+    const bool ar_on = !STREAM && ar != nullptr && ar->world > 1;
     constexpr int CQ = GS / 4;
     using GE = Geo<BITS, CQ>;
     constexpr int NWORD = GE::NWORD, NCLASS = GE::NCLASS, NMMA = GE::NMMA;
@@ -151,6 +167,7 @@ __device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, ui
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + (size_t)p.stages * p.slot_bytes);
     uint64_t* empty_bar = full_bar + kMaxStages;
     float* xsc = reinterpret_cast<float*>(empty_bar + kMaxStages);
+    uint32_t* ar_epoch_s = reinterpret_cast<uint32_t*>(&empty_bar[kMaxStages - 1]);  // scratch (one-call plans use < kMaxStages stages)
     float* ysum = xsc + kCW * (CPW * S * MT);
 
     STAMP(0);
@@ -250,6 +267,11 @@ __device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, ui
 
         if constexpr (!STREAM) griddep_wait();  // x (and y) belong to the previous kernels of the stream
         STAMP(1);
+        if constexpr (!STREAM) {
+            // epoch of a fused all-reduce: advanced by the last CTA of the previous such launch, complete by now
+            if (ar_on && threadIdx.x == 0)
+                *ar_epoch_s = *reinterpret_cast<volatile uint32_t*>(ar->flags[ar->rank] + ar->world * kArMaxCtas) + 1u;
+        }
 
         // ---- stationary operands: digit fragments of the activations, per-group power-of-two factors, group sums
         uint32_t bfr[MT][CPW][NCLASS][NMMA][2];
@@ -520,9 +542,53 @@ __device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, ui
                 tot += __shfl_xor_sync(0xffffffffu, tot, 1);
                 tot += __shfl_xor_sync(0xffffffffu, tot, 2);
                 if (q4 == 0 && r < rows && m < p.M) {
-                    float v = __bfloat162float(__float2bfloat16_rn(tot));
-                    if (p.bias != nullptr) v = __fadd_rn(v, __bfloat162float(p.bias[r0 + r]));
-                    p.y[(size_t)m * p.N + r0 + r] = __float2bfloat16_rn(v);
+                    if (ar_on) {
+                        // row-parallel shard: the fp32 partial (+ this rank's bias share) goes to every peer
+                        if (p.bias != nullptr) tot += __bfloat162float(p.bias[r0 + r]);
+                        const uint32_t epoch = *ar_epoch_s;
+                        const size_t at = (size_t)(epoch & 1u) * ar->half_elems + ((size_t)ar->rank * p.M + m) * p.N + r0 + r;
+                        const unsigned long long word = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(tot);
+                        for (int d = 0; d < ar->world; d++)
+                            asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(ar->stage[d] + at), "l"(word) : "memory");
+                    } else {
+                        float v = __bfloat162float(__float2bfloat16_rn(tot));
+                        if (p.bias != nullptr) v = __fadd_rn(v, __bfloat162float(p.bias[r0 + r]));
+                        p.y[(size_t)m * p.N + r0 + r] = __float2bfloat16_rn(v);
+                    }
+                }
+            }
+        }
+    }
+    if constexpr (!STREAM) {
+        if (ar_on) {
+            const uint32_t epoch = *ar_epoch_s;
+            uint32_t* ctl = ar->flags[ar->rank] + ar->world * kArMaxCtas;
+            const unsigned long long* st = ar->stage[ar->rank] + (size_t)(epoch & 1u) * ar->half_elems;
+            const unsigned long long t0 = gtime();
+            for (int i = threadIdx.x; i < rows * p.M; i += kThreads) {
+                const int m = i / rows, r = i - m * rows;
+                float acc = 0.f;
+                for (int w = 0; w < ar->world; w++) {
+                    const unsigned long long* src = st + ((size_t)w * p.M + m) * p.N + r0 + r;
+                    unsigned long long v;
+                    for (;;) {
+                        asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+                        if ((uint32_t)(v >> 32) == epoch) break;
+                        if (gtime() - t0 > 4000000000ull) {  // 4 s: a peer is gone; flag the error, never hang the device
+                            atomicExch(ctl + 2, 1u);
+                            break;
+                        }
+                    }
+                    acc += __uint_as_float((uint32_t)v);
+                }
+                p.y[(size_t)m * p.N + r0 + r] = __float2bfloat16_rn(acc);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                if (atomicAdd(ctl + 1, 1u) == gridDim.x - 1u) {  // last CTA of the launch: advance the epoch
+                    ctl[1] = 0u;
+                    __threadfence();
+                    *reinterpret_cast<volatile uint32_t*>(ctl) = epoch;
                 }
             }
         }

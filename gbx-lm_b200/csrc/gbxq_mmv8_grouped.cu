@@ -46,11 +46,11 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) mmv8_grouped_kernel(const 
 template <int GS, int MT, int CPW, int R>
 int launch_inst(const GroupParams& gp, int grid, size_t smem, cudaStream_t st) {
     auto kern = mmv8_grouped_kernel<GS, MT, CPW, R>;
-    static bool configured = false;  // benign race: attribute set is idempotent
-    if (!configured) {
+    static DeviceOnce configured;  // per device: the attribute is a per-device property
+    if (configured.need()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
         if (e != cudaSuccess) return check_cuda(e);
-        configured = true;
+        configured.done();
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);

@@ -408,11 +408,11 @@ Plan make_plan(int64_t N, int64_t K, int bits, int gs) {
 template <int BITS, int QW, bool SB_TMA>
 int launch_inst2(const CUtensorMap& tw, const CUtensorMap& ts, const CUtensorMap& tb, const SkinnyParams& p, size_t smem, int grid,
                  cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;  // per device: the attribute is a per-device property
+    if (configured.need()) {
         cudaError_t e = cudaFuncSetAttribute(skinny_kernel<BITS, QW, SB_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return check_cuda(e);
-        configured = true;
+        configured.done();
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);

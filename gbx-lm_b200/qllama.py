@@ -167,7 +167,7 @@ class Attention(nn.Module):  # gbx_lm/models/qllama.py:39-96
             ops.rope_cache(qh, k.view(B, self.n_kv_heads, self.head_dim), v.view(B, self.n_kv_heads, self.head_dim),
                            positions, self.rope.inv_freq, cache.keys, cache.values)
             out = ops.decode_attention(qh, cache.keys, cache.values, positions, self.scale, attend_len)
-            return self.tp.all_reduce(self.o_proj(out.view(B, 1, -1)))
+            return self.tp.row_parallel(self.o_proj, out.view(B, 1, -1))
         q = q.view(B, L, self.n_heads, -1).transpose(1, 2)
         k = k.view(B, L, self.n_kv_heads, -1).transpose(1, 2)
         v = v.view(B, L, self.n_kv_heads, -1).transpose(1, 2)
@@ -185,7 +185,7 @@ class Attention(nn.Module):  # gbx_lm/models/qllama.py:39-96
         out = F.scaled_dot_product_attention(q, keys, values, attn_mask=mask[None, None], scale=self.scale,
                                              enable_gqa=self.n_heads != self.n_kv_heads)
         out = out.transpose(1, 2).reshape(B, L, -1)
-        return self.tp.all_reduce(self.o_proj(out))
+        return self.tp.row_parallel(self.o_proj, out)
 
 
 class MLP(nn.Module):  # gbx_lm/models/qllama.py:99-115
@@ -205,7 +205,7 @@ class MLP(nn.Module):  # gbx_lm/models/qllama.py:99-115
             act = ops.silu_mul(gate, up)
         else:
             act = F.silu(gate) * up
-        return self.tp.all_reduce(self.down_proj(act))
+        return self.tp.row_parallel(self.down_proj, act)
 
 
 class TransformerBlock(nn.Module):  # gbx_lm/models/qllama.py:118-141

@@ -23,11 +23,22 @@ ROW_PARALLEL = ("o_proj", "down_proj")
 class TPContext:
     """Rank/world of the tensor-parallel group + the all-reduce used after row-parallel layers."""
 
-    def __init__(self, rank: int = 0, world: int = 1, group=None, oneshot: "Optional[OneShotAllReduce]" = None):
+    def __init__(self, rank: int = 0, world: int = 1, group=None, oneshot: "Optional[OneShotAllReduce]" = None,
+                 fused: "Optional[FusedRowParallel]" = None):
         self.rank = rank
         self.world = world
         self.group = group
         self.oneshot = oneshot
+        self.fused = fused
+
+    def row_parallel(self, layer, x: torch.Tensor) -> torch.Tensor:
+        """y = all-reduce(x_shard . W_shard^T) of a row-parallel QuantizedLinear (o_proj / down_proj): ONE kernel when the
+        decode kernel serves the call (gbxq_qmm_rowpar_allreduce), otherwise the matmul followed by the all-reduce."""
+        if self.world > 1 and self.fused is not None:
+            y = self.fused(layer, x)
+            if y is not None:
+                return y
+        return self.all_reduce(layer(x))
 
     def all_reduce(self, y: torch.Tensor) -> torch.Tensor:
         if self.world == 1:
@@ -147,3 +158,63 @@ class OneShotAllReduce:
         )
         _lib.check(rc, "gbxq_allreduce_oneshot")
         return y
+
+
+class FusedRowParallel:
+    """Row-parallel QuantizedLinear with the all-reduce inside the matmul kernel (gbxq_qmm_rowpar_allreduce): fp32
+    staging buffers and epoch flags in torch symmetric memory, addressed by every peer over NVLink."""
+
+    def __init__(self, group, device: torch.device, max_elems: int = 4 * 8192):
+        import ctypes
+
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        from . import _lib
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.world = dist.get_world_size(self.group)
+        self.stage_elems = 2 * self.world * max_elems  # two halves x world partials of [M, N], 8-byte {fp32, epoch} words
+        self.stage = symm.empty((self.stage_elems,), dtype=torch.int64, device=device)
+        self.stage.zero_()
+        self.shdl = symm.rendezvous(self.stage, self.group.group_name)
+        self.flags = symm.empty((self.world * _lib.RP_MAX_CTAS + 4,), dtype=torch.int32, device=device)
+        self.flags.zero_()
+        self.fhdl = symm.rendezvous(self.flags, self.group.group_name)
+        self._stage_ptrs = (ctypes.c_void_p * self.world)(*[self.shdl.buffer_ptrs[r] for r in range(self.world)])
+        self._flag_ptrs = (ctypes.c_void_p * self.world)(*[self.fhdl.buffer_ptrs[r] for r in range(self.world)])
+        self.comm = _lib.Comm(self._stage_ptrs, self._flag_ptrs, self.stage_elems, self.rank, self.world)
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)
+
+    def timed_out(self) -> bool:
+        from . import _lib
+
+        return bool(self.flags[self.world * _lib.RP_MAX_CTAS + 2].item())
+
+    def __call__(self, layer, x: torch.Tensor) -> Optional[torch.Tensor]:
+        """Returns the reduced y, or None when the fused kernel does not serve this call (nothing was enqueued)."""
+        import ctypes
+
+        from . import _lib
+
+        if x.dtype != torch.bfloat16 or layer.scales.dtype != torch.bfloat16:
+            return None
+        k = layer.input_dims
+        x2 = x.reshape(-1, k)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        m, n = x2.shape[0], layer.output_dims
+        if m > 4 or 2 * self.world * m * n > self.stage_elems:
+            return None
+        y = torch.empty((m, n), dtype=torch.bfloat16, device=x.device)
+        bias = getattr(layer, "bias", None)
+        rc = _lib.get().gbxq_qmm_rowpar_allreduce(
+            x2.data_ptr(), layer.qweight.data_ptr(), layer.scales.data_ptr(), layer.zeros.data_ptr(),
+            bias.data_ptr() if bias is not None else None, y.data_ptr(), m, n, k, layer.bits, layer.group_size, 0,
+            ctypes.byref(self.comm), torch.cuda.current_stream().cuda_stream)
+        if rc == -9:
+            return None
+        _lib.check(rc, "gbxq_qmm_rowpar_allreduce")
+        return y.reshape(*x.shape[:-1], n)

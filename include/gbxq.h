@@ -233,13 +233,47 @@ int gbxq_silu_mul(const void* gate, const void* up, void* out, int64_t n, void* 
  *                                                every rank), may alias `in`
  *   seq : starts at 1, increases by exactly 1 per call, same on every rank; or 0 on every call: the sequence
  *         number is then kept on the device in entry world*GBXQ_AR_MAX_CTAS of this rank's flag array (flag arrays
- *         need world*GBXQ_AR_MAX_CTAS + 2 entries), which makes the call replayable from a CUDA graph.
+ *         need world*GBXQ_AR_MAX_CTAS + 3 entries), which makes the call replayable from a CUDA graph.  Entry
+ *         world*GBXQ_AR_MAX_CTAS + 2 is set to 1 if a wait for a peer ever timed out (4 s): results are then undefined,
+ *         the device never hangs.
  * Every rank must enqueue the call with the same count/dtype/seq on a stream of its own device.
  */
 #define GBXQ_AR_MAX_CTAS 32
 int gbxq_allreduce_oneshot(const void* in, void* out, int64_t count, int dtype,
                            void* const* peer_bufs_dev, uint32_t* const* peer_flags_dev,
                            int64_t capacity, int rank, int world, uint32_t seq, void* stream);
+
+/*
+ * Row-parallel QuantizedLinear with the all-reduce INSIDE the matmul kernel (o_proj / down_proj under tensor
+ * parallelism: gbx_lm/models/qllama.py:96,115 are the call sites that get K-sharded; new work).
+ * Rank r holds the K-slice [r*K/world, (r+1)*K/world) of the layer (`K` below is that LOCAL size) and a slice of x;
+ * the result y[M,N] = sum over ranks of x_r . dequant(W_r)^T (+ bias) is identical on every rank.
+ * One launch per rank: each CTA of the decode kernel pushes the fp32 partial sums of the output rows it owns into
+ * every peer's staging buffer (P2P stores over NVLink) and adds the `world` partials of those rows in rank order,
+ * rounding once to T.  A partial travels as one 8-byte word {fp32 bits, epoch} and the receiver polls the word itself
+ * (no fence, no flag: one NVLink one-way latency).  No second kernel, no NCCL call; the exchange of a CTA overlaps the
+ * matmul of the others.
+ *   comm->peer_stage_host : HOST array [world]; entry r = rank r's staging buffer of `stage_elems` 8-byte words,
+ *                           8-byte aligned, ZEROED ONCE, mapped into this process (symmetric memory).
+ *                           Needs stage_elems >= 2 * world * M * N.
+ *   comm->peer_flags_host : HOST array [world]; entry r = rank r's uint32 array of world * GBXQ_RP_MAX_CTAS + 4
+ *                           entries, zeroed once (only the control words at [world*GBXQ_RP_MAX_CTAS ..] of the own
+ *                           rank are used: epoch, CTAs done, error).  Entry +2 becomes 1 if a wait timed out (4 s).
+ * Every rank must enqueue the same call (same M, N, bits, group_size) in the same order.  `bias`, if given, is added
+ * by the rank that holds it (pass NULL on the others).  CUDA-graph capturable (the epoch lives in the flag array).
+ * Returns GBXQ_EUNSUPPORTED (nothing enqueued) when the decode kernel cannot serve the arguments (M > 4, 3-/6-bit,
+ * non-bf16): use gbxq_qmm followed by gbxq_allreduce_oneshot then.
+ */
+#define GBXQ_RP_MAX_CTAS 512
+typedef struct gbxq_comm {
+    void* const* peer_stage_host;
+    uint32_t* const* peer_flags_host;
+    int64_t stage_elems;
+    int rank, world;
+} gbxq_comm;
+int gbxq_qmm_rowpar_allreduce(const void* x, const uint32_t* qweight, const void* scales, const void* biases,
+                              const void* bias /* nullable */, void* y, int64_t M, int64_t N, int64_t K, int bits,
+                              int group_size, int dtype, const gbxq_comm* comm, void* stream);
 
 #ifdef __cplusplus
 }

@@ -9,6 +9,27 @@ import torch
 from oracle import mlx_affine as A
 
 
+def dense_weights_c(ckpt: dict, plan_bits, device="cpu"):
+    """As dense_weights, through the C/OpenMP oracle (bit-identical to the numpy one, tests/test_oracle.py) and moved to
+    `device` layer by layer: for full-size architectures (Llama-3.2-1B: 1.2e9 weights)."""
+    from oracle import c_oracle as C
+
+    out = {}
+    for m in sorted({k.rsplit(".", 1)[0] for k in ckpt if k.endswith(".qweight")}):
+        bits, gs = plan_bits(m)
+        qw = ckpt[m + ".qweight"].view(torch.int32).numpy().view(np.uint32)
+        s = ckpt[m + ".scales"].view(torch.int16).numpy().view(np.uint16)
+        z = ckpt[m + ".zeros"].view(torch.int16).numpy().view(np.uint16)
+        d = C.dequantize(qw, s, z, gs, bits, "bf16")  # uint16 bf16 bit patterns
+        out[m + ".weight"] = torch.from_numpy(d.view(np.int16)).view(torch.bfloat16).to(device).float()
+        if m + ".bias" in ckpt:
+            out[m + ".bias"] = ckpt[m + ".bias"].to(device).float()
+    for k, v in ckpt.items():
+        if k.rsplit(".", 1)[1] not in ("qweight", "scales", "zeros", "bias") or k.endswith("norm.bias"):
+            out[k] = v.to(device).float()
+    return out
+
+
 def dense_weights(ckpt: dict, plan_bits):
     """ckpt: name -> tensor (cpu). plan_bits(module_name) -> (bits, gs). Returns fp32 dense dict."""
     out = {}
@@ -59,7 +80,9 @@ def forward(W, cfg, tokens):
     eps = cfg["rms_norm_eps"]
     inv = _inv_freq(hd, cfg["rope_theta"], cfg.get("rope_scaling"))
     B, L = tokens.shape
-    pos = torch.arange(L)
+    dev = tokens.device
+    inv = inv.to(dev)
+    pos = torch.arange(L, device=dev)
     h = W["model.embed_tokens.weight"][tokens]
     lin = lambda x, name: torch.nn.functional.linear(x, W[name + ".weight"], W.get(name + ".bias"))
     for i in range(cfg["num_hidden_layers"]):
@@ -72,7 +95,7 @@ def forward(W, cfg, tokens):
         k = k.repeat_interleave(nh // nkv, 1)
         v = v.repeat_interleave(nh // nkv, 1)
         att = (q @ k.transpose(-1, -2)) * hd ** -0.5
-        att = att.masked_fill(torch.triu(torch.ones(L, L, dtype=torch.bool), 1), float("-inf")).softmax(-1)
+        att = att.masked_fill(torch.triu(torch.ones(L, L, dtype=torch.bool, device=dev), 1), float("-inf")).softmax(-1)
         o = (att @ v).transpose(1, 2).reshape(B, L, -1)
         h = h + lin(o, p + "self_attn.o_proj")
         x = _rms(h, W[p + "post_attention_layernorm.weight"], eps)

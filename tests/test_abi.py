@@ -164,7 +164,7 @@ def test_stream_plan_blob_invariants():
         2: [call(4096, [(4, 4096, 128), (4, 1024, 128)]), call(8192, [(8, 4096, 128)])],
         4: [call(4096, [(4, 6144, 64)]), call(2048, [(2, 2048, 64), (4, 512, 64)])],
     }
-    P, CALL = 136, 608  # sizeof(Mmv8Params), sizeof(StreamCallDev)
+    P, CALL = 144, 640  # sizeof(Mmv8Params), sizeof(StreamCallDev)
     for M, calls in chains.items():
         arr = (_lib.StreamCall * len(calls))(*calls)
         info = _lib.StreamInfo()
@@ -186,7 +186,7 @@ def test_stream_plan_blob_invariants():
                 po = off + s * P
                 xq, wq, sq, bq, biasq, yq, N, K = struct.unpack_from("6Q2q", raw, po)
                 Mv, G, row_bytes, nch, cw, rg, tr, stages, slot_bytes, sb_off, early = struct.unpack_from("2i2I4i2Ii", raw, po + 64)
-                rows_base, rows_rem, spr0, spr1 = struct.unpack_from("4i", raw, po + 120)
+                rows_base, rows_rem, spr0, spr1 = struct.unpack_from("4i", raw, po + 128)
                 sg = c.segs[s]
                 grid_s = cta0[s + 1] - cta0[s]
                 assert (N, K, bits[s], Mv) == (sg.N, c.K, sg.bits, M) and wq == sg.qweight and xq == c.x
