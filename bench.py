@@ -36,6 +36,18 @@ METRIC = "qmatmul_hbm_gbs_m1"
 UNIT = "GB/s"
 
 
+def load_tensor_peak():
+    """Sustained dense bf16 peak (the GEMM is timed inside a long step), MEASURED_PEAKS.json else the profiling guide's fallback."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+        except Exception:
+            pass
+    return 1400.0, "fallback (B200_PROFILING.md)"
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -199,7 +211,8 @@ def run_gbxq(args):
 
     ops.set_pdl_mode(args.pdl)
     dims, full_plan = build_plan(args)
-    M = args.batch
+    prefill = args.phase == "prefill"
+    M = args.prefill_tokens if prefill else args.batch
     # --parallelism: how N > 1 GPUs are used.  tp = tensor-parallel shards of ONE model instance (column-parallel
     # q/k/v/gate/up, row-parallel o/down + sum all-reduce; strong scaling) -- what the 32B / 70B configurations need;
     # dp = one full model replica per GPU, independent decode streams, no data-path collective (weak scaling) -- the
@@ -384,11 +397,18 @@ def run_gbxq(args):
     # per-launch algorithmic bytes / per-launch average duration == per-rank bytes / step time
     rank_bytes = sum(W.qmm_bytes(M, n, k, b, g) for (_, _, n, k, b, g) in plan)
     achieved = rank_bytes / (ms_step * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
+    # DRAM traffic per launch comes from an ncu capture of the SAME command (tools/traffic_from_ncu.py writes
+    # profiles/traffic.json with the workload it was taken on); it is reported only when this run is that workload
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            same = (tj.get("model", "llama-3-8b") == args.model and tj.get("strategy", "bpw-4.0") == args.strategy and
+                    int(tj.get("batch", 1)) == args.batch and world == 1 and not prefill and not args.stream)
+            if same:
+                traffic = tj.get("dram_bytes_per_launch")
+                traffic_src = tj.get("source")
         except Exception:
             traffic = None
 
@@ -419,7 +439,7 @@ def run_gbxq(args):
         },
         "decode_tok_s_qmm_only": round(1e3 / ms_step * M * replicas, 2),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                     "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "kernel": ("gbxq::stream_kernel (persistent chain launch: the mmv8 body over every call of the step)"
                                 if args.stream else "gbxq::mmv8_kernel / mmv8_grouped_kernel (all launches of the step)"),
                      "bytes_per_launch_avg": rank_bytes // max(launches_per_step, 1),
@@ -431,7 +451,29 @@ def run_gbxq(args):
         "also": also,
         "clocks": clocks,
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if prefill:
+        # prefill leg: the same 7*L forwards at M = prefill chunk (gbx_lm/utils.py:312-319: 2048-token chunks), a dense
+        # contraction on the tcgen05 kernel: TFLOP/s (2*M*N*K per forward; dequant ALU work not counted) against the
+        # measured sustained bf16 peak
+        flops = sum(2.0 * M * n * k for (_, _, n, k, _, _) in full_plan) * replicas
+        rank_flops = sum(2.0 * M * n * k for (_, _, n, k, _, _) in plan)
+        tpeak, tsrc = load_tensor_peak()
+        tf = flops / (ms_step * 1e-3) / 1e12
+        line.update({"metric": "qmatmul_prefill_tflops", "value": round(tf, 2), "unit": "TFLOP/s"})
+        line["config"]["workload"] = (f"{args.model} layer-mix {args.strategy} prefill chunk of {M} tokens: {len(full_plan)} "
+                                      f"QuantizedLinear forwards/step (stored bpw {W.stored_bpw(full_plan):.3f})")
+        line["config"]["flops_per_step"] = flops
+        line["config"]["l2"] = "weights + activations per step >> 126 MB L2"
+        line.pop("decode_tok_s_qmm_only", None)
+        line["prefill_tok_s_qmm_only"] = round(M * replicas / (ms_step * 1e-3), 1)
+        ach = rank_flops / (ms_step * 1e-3) / 1e12
+        line["roofline"] = {"bound": "tensor", "achieved": round(ach, 2), "peak": tpeak, "unit": "TFLOP/s", "frac": round(ach / tpeak, 4),
+                            "traffic": None, "peak_source": tsrc, "kernel": "gbxq::gemm_kernel (tcgen05.mma swap-AB, in-kernel dequant)",
+                            "flops_per_launch_avg": rank_flops / max(launches_per_step, 1),
+                            "avg_launch_us": round(ms_step * 1e3 / max(launches_per_step, 1), 3)}
+        line["e2e"]["value"] = round(flops / (e2e_ms * 1e-3) / 1e12, 2)
+        line["e2e"]["unit"] = "TFLOP/s"
+    if world == 1 and not args.no_cpu_baseline and not prefill:
         line["cpu_baseline"] = cpu_sample(args, layers_for_cpu=[(p, m) for (p, m) in layers[:7]], M=M, budget_s=args.cpu_seconds)
     print(json.dumps(line), flush=True)
     finish()
@@ -528,6 +570,8 @@ def main():
     ap.add_argument("--bits", type=int, default=4)
     ap.add_argument("--group-size", type=int, default=64)
     ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--phase", default="decode", choices=["decode", "prefill"], help="prefill: the forwards at M = --prefill-tokens, reported in TFLOP/s against the tensor roofline")
+    ap.add_argument("--prefill-tokens", type=int, default=2048)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--grouped", type=int, default=1, help="1: q|k|v and gate|up as one gbxq_qmm_grouped call each (as the model does)")

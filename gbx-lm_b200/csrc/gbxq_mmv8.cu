@@ -158,6 +158,10 @@ int launch_mmv8_ar(const void* x, const uint32_t* w, const void* s, const void* 
         case 4064: return launch_mt<4, 64>(p, ar, pl, st);
         case 4128: return launch_mt<4, 128>(p, ar, pl, st);
         case 4032: return launch_mt<4, 32>(p, ar, pl, st);
+        case 3064: return launch_mt<3, 64>(p, ar, pl, st);
+        case 3128: return launch_mt<3, 128>(p, ar, pl, st);
+        case 6064: return launch_mt<6, 64>(p, ar, pl, st);
+        case 6128: return launch_mt<6, 128>(p, ar, pl, st);
         case 2064: return launch_mt<2, 64>(p, ar, pl, st);
         case 2128: return launch_mt<2, 128>(p, ar, pl, st);
         case 8064: return launch_mt<8, 64>(p, ar, pl, st);

@@ -60,23 +60,27 @@ __device__ __forceinline__ float lds_bf16(const uint8_t* addr) {
 // ---- packing geometry.  A thread chunk = CQ = group_size/4 codes of one (row, group).  NMMA MMAs per chunk and
 //      accumulator class; MMA u of class c takes A registers areg(c, u, 0) [k-slots 4t..4t+3] and areg(c, u, 1)
 //      [k-slots 16+4t..]; byte i of such a register is code code_of(c, u, half, i) of the chunk.
+//      The 3- and 6-bit packings (codes straddle bytes and words: quantized_linear_gba.py:61, 8 codes / 3 bytes and
+//      4 codes / 3 bytes) are realigned to one byte per code right after the shared-memory load (load_chunk) and run
+//      through the 8-bit geometry from there: EB = the width of a code once it sits in registers.
 template <int BITS, int CQ> struct Geo {
-    static constexpr int NWORD = CQ * BITS / 32;
-    static constexpr int NCLASS = BITS == 8 ? 1 : 2;
+    static constexpr int EB = (BITS == 3 || BITS == 6) ? 8 : BITS;
+    static constexpr int NWORD = CQ * EB / 32;
+    static constexpr int NCLASS = EB == 8 ? 1 : 2;
     static constexpr int NREG = CQ / 4;                    // A registers (4 codes each) per chunk
     static constexpr int NMMA = (NREG / NCLASS + 1) / 2;   // k32 MMAs per class (a lone register pairs with zero)
     static constexpr bool HALF = (NREG / NCLASS) % 2 == 1; // last MMA of a class has no second register
-    static constexpr int CMUL = BITS == 8 ? 1 : (BITS == 4 ? 16 : 4);  // T = CMUL * D0 + D1; scale / CMUL
+    static constexpr int CMUL = EB == 8 ? 1 : (EB == 4 ? 16 : 4);  // T = CMUL * D0 + D1; scale / CMUL
     __host__ __device__ static constexpr int code_of(int c, int u, int half, int i) {
-        if (BITS == 8) return 8 * u + 4 * half + i;                       // word 2u+half, byte i
-        if (BITS == 4) return 16 * u + 8 * half + 2 * i + c;              // word 2u+half, nibble 2i+c
+        if (EB == 8) return 8 * u + 4 * half + i;                         // word 2u+half, byte i
+        if (EB == 4) return 16 * u + 8 * half + 2 * i + c;                // word 2u+half, nibble 2i+c
         return 16 * u + 4 * i + 2 * half + c;                             // 2-bit: word u, field 4i + 2*half + c
     }
 };
 
 template <int BITS, int CQ>
 __device__ __forceinline__ uint32_t areg(const uint32_t (&w)[Geo<BITS, CQ>::NWORD], int c, int u, int half) {
-    if constexpr (BITS == 8) {
+    if constexpr (Geo<BITS, CQ>::EB == 8) {
         return w[2 * u + half];
     } else if constexpr (BITS == 4) {
         const uint32_t word = w[2 * u + half];
@@ -84,6 +88,54 @@ __device__ __forceinline__ uint32_t areg(const uint32_t (&w)[Geo<BITS, CQ>::NWOR
     } else {
         const uint32_t word = half == 0 ? w[u] : (w[u] >> 4);
         return c == 0 ? (word & 0x03030303u) : (word & 0x0c0c0c0cu);
+    }
+}
+
+// bits [pos, pos + 32) of a little-endian word stream (only as many as the caller masks are meaningful)
+template <int NR> __device__ __forceinline__ uint32_t bit_window(const uint32_t (&r)[NR], int pos) {
+    const int i = pos >> 5, off = pos & 31;
+    if (off == 0) return r[i];
+    if (i + 1 < NR) return __funnelshift_r(r[i], r[i + 1], off);
+    return r[i] >> off;
+}
+// four 3-bit fields (bits 0..11 of x) -> one byte each.  Even and odd fields are spread by one multiply each (the
+// shifted copies do not overlap, so the adds inside the multiply carry nothing) and masked into place.
+__device__ __forceinline__ uint32_t spread3(uint32_t x) {
+    const uint32_t e = (x & 0x1c7u) * 0x401u;    // f0 @0, f2 @6 | f0 @10, f2 @16
+    const uint32_t o = (x & 0xe38u) * 0x8020u;   // f1 @8, f3 @14 | f1 @18, f3 @24
+    return (e & 0x00070007u) | (o & 0x07000700u);
+}
+// four 6-bit fields (bits 0..23 of x) -> one byte each
+__device__ __forceinline__ uint32_t spread6(uint32_t x) {
+    return (x & 0x3fu) | ((x << 2) & 0x3f00u) | ((x << 4) & 0x3f0000u) | ((x << 6) & 0x3f000000u);
+}
+
+// The thread chunk at shared-memory address `addr` as A-operand words: packed words as they are for 2/4/8-bit,
+// one byte per code for 3/6-bit.  3-bit chunks of 16 codes are 6 bytes long and only 2-byte aligned.
+template <int BITS, int CQ>
+__device__ __forceinline__ void load_chunk(const uint8_t* addr, uint32_t (&w)[Geo<BITS, CQ>::NWORD]) {
+    if constexpr (BITS == 3 || BITS == 6) {
+        constexpr int RAWB = CQ * BITS / 8;           // 6, 12 (3-bit) or 12, 24 (6-bit) bytes
+        constexpr int NR = (RAWB + 3) / 4 + (RAWB % 4 ? 0 : 0);
+        uint32_t r[RAWB == 6 ? 2 : NR];
+        if constexpr (RAWB == 6) {
+            const uintptr_t a = reinterpret_cast<uintptr_t>(addr);
+            const uint32_t* al = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+            const uint32_t r0 = al[0], r1 = al[1];
+            const uint32_t sh = (uint32_t)(a & 3) * 8u;  // 0 or 16
+            r[0] = __funnelshift_r(r0, r1, sh);
+            r[1] = r1 >> sh;
+        } else {
+#pragma unroll
+            for (int i = 0; i < NR; i++) r[i] = reinterpret_cast<const uint32_t*>(addr)[i];
+        }
+#pragma unroll
+        for (int j = 0; j < CQ / 4; j++) {
+            if constexpr (BITS == 3) w[j] = spread3(bit_window(r, 12 * j));
+            else w[j] = spread6(bit_window(r, 24 * j));
+        }
+    } else {
+        lds_words<Geo<BITS, CQ>::NWORD>(addr, w);
     }
 }
 
@@ -410,8 +462,8 @@ __device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, ui
             auto unit = [&](int q, int j) {
                 const uint8_t* rbase = slot + (uint32_t)(lrow0 + q * W) * p.row_bytes + j * colstride;
                 uint32_t wa[NWORD], wb[NWORD];
-                lds_words<NWORD>(rbase + offA, wa);
-                lds_words<NWORD>(rbase + offB, wb);
+                load_chunk<BITS, CQ>(rbase + offA, wa);
+                load_chunk<BITS, CQ>(rbase + offB, wb);
                 const float sc = lds_bf16(sslot + (uint32_t)(lrow0 + q * W) * g2 + j * sstride + sofT);
                 const int kZero4[4] = {0, 0, 0, 0};
                 int T[MT][2];  // [token][part]: 256 * hi + lo of the meaningful part's group
@@ -620,8 +672,8 @@ inline int env_int(const char* name, int dflt) {
 // grid_want > 0: the number of CTAs this layer may use (a segment of a grouped launch); 0: the whole device
 inline Plan make_plan(int64_t M, int64_t N, int64_t K, int bits, int gs, int grid_want = 0) {
     Plan pl{};
-    if (!(bits == 2 || bits == 4 || bits == 8) || M < 1 || M > 4 || N < 1) return pl;
-    if (bits == 2 && gs == 32) return pl;  // a thread chunk would be half a word
+    if (!(bits == 2 || bits == 3 || bits == 4 || bits == 6 || bits == 8) || M < 1 || M > 4 || N < 1) return pl;
+    if ((bits == 2 || bits == 3 || bits == 6) && gs == 32) return pl;  // a thread chunk would be a fraction of a word
     const int64_t G = K / gs;
     if (G % 8) return pl;  // S | G, and 16-byte rows of scales for the bulk copies
     const int64_t row_bytes = K * bits / 8;

@@ -38,6 +38,8 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) mmv8_grouped_kernel(const 
     // one copy of the body per bit width; the switch is CTA-uniform
     switch (gp.bits[s]) {
         case 2: mmv8_body<2, GS, MT, CPW, R>(gp.seg[s], bid, smem); break;
+        case 3: mmv8_body<3, GS, MT, CPW, R>(gp.seg[s], bid, smem); break;
+        case 6: mmv8_body<6, GS, MT, CPW, R>(gp.seg[s], bid, smem); break;
         case 4: mmv8_body<4, GS, MT, CPW, R>(gp.seg[s], bid, smem); break;
         default: mmv8_body<8, GS, MT, CPW, R>(gp.seg[s], bid, smem); break;
     }
@@ -108,7 +110,7 @@ int launch_mmv8_grouped(const gbxq_segment* segs, int nseg, const void* x, int64
     double bytes[GBXQ_MAX_SEGMENTS], total = 0;
     for (int i = 0; i < nseg; i++) {
         const gbxq_segment& sg = segs[i];
-        if (sg.group_size != gs || !(sg.bits == 2 || sg.bits == 4 || sg.bits == 8) || sg.N < 1) return GBXQ_EUNSUPPORTED;
+        if (sg.group_size != gs || !(sg.bits == 2 || sg.bits == 3 || sg.bits == 4 || sg.bits == 6 || sg.bits == 8) || sg.N < 1) return GBXQ_EUNSUPPORTED;
         if (((uintptr_t)sg.qweight | (uintptr_t)sg.scales | (uintptr_t)sg.biases) & 15) return GBXQ_EUNSUPPORTED;
         if ((uintptr_t)sg.y & 1) return GBXQ_EUNSUPPORTED;
         bytes[i] = segment_cost(sg.N, K, sg.bits, gs);

@@ -105,8 +105,8 @@ def test_qmm_vs_oracle_small(cuda_device, kernel, bits, gs):
 
 
 def _mmv_ok(bits, gs, K=1024, kernel="mmv"):
-    if kernel == "mmv8":
-        return bits in (2, 4, 8) and not (bits == 2 and gs == 32) and (K // gs) % 8 == 0
+    if kernel == "mmv8":  # every packing width; 2/3/6-bit need a whole word per thread chunk (gs >= 64)
+        return not (bits in (2, 3, 6) and gs == 32) and (K // gs) % 8 == 0
     return bits in (2, 4, 8) and gs * bits // 32 in (4, 8, 16) and (K // gs) % 8 == 0
 
 
@@ -114,7 +114,7 @@ MMV_KERNELS = ("mmv", "mmv8")
 
 
 @pytest.mark.parametrize("kernel", MMV_KERNELS)
-@pytest.mark.parametrize("bits", (2, 4, 8))
+@pytest.mark.parametrize("bits", (2, 3, 4, 6, 8))
 @pytest.mark.parametrize("gs", GS)
 def test_qmm_mmv_vs_oracle_small(cuda_device, kernel, bits, gs):
     """Tensor-pipe decode kernels ("slice" MMA layout; bf16 HMMA and integer IMMA) at M = 1..4, every supported packing."""
@@ -456,7 +456,7 @@ def test_qmm_grouped_matches_single_calls_and_oracle(cuda_device, M, gs):
 
     K = 2048
     for combo in (((4, 512), (4, 128), (4, 128)), ((2, 1024), (4, 1024)), ((8, 96), (2, 300), (4, 1), (4, 149)),
-                  ((4, 256), (3, 128)), ((4, 4096), (2, 4096))):
+                  ((4, 256), (3, 128)), ((4, 4096), (2, 4096)), ((2, 512), (2, 128), (6, 128)), ((3, 300), (6, 77))):
         segs, raw = [], []
         for i, (bits, N) in enumerate(combo):
             L = A.synth_layer(N, K, bits, gs, seed=7 * i + bits + N, with_bias=(i == 1))
@@ -467,7 +467,7 @@ def test_qmm_grouped_matches_single_calls_and_oracle(cuda_device, M, gs):
         n0 = ops.launch_count()
         ys = g.quantized_matmul_grouped(x, segs)
         launches = ops.launch_count() - n0
-        fusable = M <= 2 and all(b in (2, 4, 8) for b, _ in combo)  # M >= 3 goes to the 8-token skinny kernel per segment
+        fusable = M <= 2  # every width shares one launch (3-/6-bit are realigned in registers); M >= 3: skinny kernel per segment
         # the per-segment fallback may tile M inside a segment (3-/6-bit GEMV: M tiles of 1/2), so only a lower bound there
         assert (launches == 1) if fusable else (launches >= len(combo)), (combo, M, launches)
         for sg, L, y, (bits, N) in zip(segs, raw, ys, combo):
