@@ -26,7 +26,10 @@ struct GroupParams {
     int nseg;
 };
 
-template <int GS, int MT, int CPW, int R>
+// ODD: the launch holds a 3- or 6-bit segment.  Those bodies (register realignment of the straddling codes) live in a
+// kernel of their own: with five bodies in one kernel the common 2/4/8-bit launches of the 8B step ran 10 % slower
+// (profiles/r02g_variants.txt: instruction footprint), although a CTA only ever executes one body.
+template <int GS, int MT, int CPW, int R, bool ODD>
 __global__ void __launch_bounds__(kThreads, kMinCtas) mmv8_grouped_kernel(const __grid_constant__ GroupParams gp) {
     extern __shared__ __align__(1024) uint8_t smem[];
     int bid = (int)blockIdx.x;
@@ -36,18 +39,27 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) mmv8_grouped_kernel(const 
         if (i < gp.nseg && bid >= gp.cta0[i]) s = i;
     bid -= gp.cta0[s];
     // one copy of the body per bit width; the switch is CTA-uniform
-    switch (gp.bits[s]) {
+    const int bits = gp.bits[s];
+    if constexpr (ODD) {
+        if (bits == 3) {
+            mmv8_body<3, GS, MT, CPW, R>(gp.seg[s], bid, smem);
+            return;
+        }
+        if (bits == 6) {
+            mmv8_body<6, GS, MT, CPW, R>(gp.seg[s], bid, smem);
+            return;
+        }
+    }
+    switch (bits) {
         case 2: mmv8_body<2, GS, MT, CPW, R>(gp.seg[s], bid, smem); break;
-        case 3: mmv8_body<3, GS, MT, CPW, R>(gp.seg[s], bid, smem); break;
-        case 6: mmv8_body<6, GS, MT, CPW, R>(gp.seg[s], bid, smem); break;
         case 4: mmv8_body<4, GS, MT, CPW, R>(gp.seg[s], bid, smem); break;
         default: mmv8_body<8, GS, MT, CPW, R>(gp.seg[s], bid, smem); break;
     }
 }
 
-template <int GS, int MT, int CPW, int R>
-int launch_inst(const GroupParams& gp, int grid, size_t smem, cudaStream_t st) {
-    auto kern = mmv8_grouped_kernel<GS, MT, CPW, R>;
+template <int GS, int MT, int CPW, int R, bool ODD>
+int launch_inst2(const GroupParams& gp, int grid, size_t smem, cudaStream_t st) {
+    auto kern = mmv8_grouped_kernel<GS, MT, CPW, R, ODD>;
     static DeviceOnce configured;  // per device: the attribute is a per-device property
     if (configured.need()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
@@ -67,6 +79,13 @@ int launch_inst(const GroupParams& gp, int grid, size_t smem, cudaStream_t st) {
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, gp);
     count_launch();
     return check_cuda(e);
+}
+
+template <int GS, int MT, int CPW, int R>
+int launch_inst(const GroupParams& gp, int grid, size_t smem, cudaStream_t st) {
+    bool odd = false;
+    for (int i = 0; i < gp.nseg; i++) odd |= gp.bits[i] == 3 || gp.bits[i] == 6;
+    return odd ? launch_inst2<GS, MT, CPW, R, true>(gp, grid, smem, st) : launch_inst2<GS, MT, CPW, R, false>(gp, grid, smem, st);
 }
 
 template <int GS, int MT>

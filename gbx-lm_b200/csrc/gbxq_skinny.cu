@@ -92,7 +92,9 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0,
 }
 
 // BITS in {2,4,8}; QW = 32-bit words per thread-quarter of a group (= group_size * BITS / 128)
-template <int BITS, int QW, bool SB_TMA>
+// NT = token octets per pass (1: up to 8 tokens, 2: up to 16): the second octet reuses the unpacked A registers, so
+// 9..16 tokens cost two more MMAs and folds per tile instead of a second pass over the weights.
+template <int BITS, int QW, bool SB_TMA, int NT>
 __global__ void __launch_bounds__(kThreads, 1)
 skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_s,
               const __grid_constant__ CUtensorMap tmap_b, const SkinnyParams p) {
@@ -168,7 +170,7 @@ skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         asm volatile("griddepcontrol.wait;" ::: "memory");  // x (and y) belong to the previous kernels of the stream
 
         struct Pre {            // per-stage operands fetched one stage ahead
-            uint4 xn[(CQ * 2 + 15) / 16];  // this thread's quarter of token g, natural order (CQ bf16)
+            uint4 xn[NT][(CQ * 2 + 15) / 16];  // this thread's quarter of tokens g (+8), natural order (CQ bf16)
             uint32_t sc[RT][2], bi[RT][2];  // raw bf16 scale / bias of rows (16q+g, 16q+g+8)
         };
         constexpr int XV = (CQ * 2 + 15) / 16;
@@ -182,11 +184,16 @@ skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
             if (nr > rb_rows) nr = rb_rows;
             const int64_t k0 = (int64_t)grp * GS + t * CQ;
             if constexpr (CQ * 2 >= 16) {
-                const uint4* src = reinterpret_cast<const uint4*>(p.x + (size_t)g * p.K + k0);
 #pragma unroll
-                for (int v = 0; v < XV; v++) pre.xn[v] = (gv && g < p.M) ? __ldg(src + v) : make_uint4(0u, 0u, 0u, 0u);
+                for (int nt = 0; nt < NT; nt++) {
+                    const int tk = g + 8 * nt;
+                    const uint4* src = reinterpret_cast<const uint4*>(p.x + (size_t)tk * p.K + k0);
+#pragma unroll
+                    for (int v = 0; v < XV; v++) pre.xn[nt][v] = (gv && tk < p.M) ? __ldg(src + v) : make_uint4(0u, 0u, 0u, 0u);
+                }
             } else {  // CQ == 4 codes (8-bit, gs 32... not instantiated) -- kept for completeness
-                pre.xn[0] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                for (int nt = 0; nt < NT; nt++) pre.xn[nt][0] = make_uint4(0u, 0u, 0u, 0u);
             }
             if constexpr (!SB_TMA) {
 #pragma unroll
@@ -203,11 +210,13 @@ skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
             }
         };
 
-        float yacc[RT][4];
+        float yacc[NT][RT][4];
 #pragma unroll
-        for (int q = 0; q < RT; q++)
+        for (int nt = 0; nt < NT; nt++)
 #pragma unroll
-            for (int e = 0; e < 4; e++) yacc[q][e] = 0.f;
+            for (int q = 0; q < RT; q++)
+#pragma unroll
+                for (int e = 0; e < 4; e++) yacc[nt][q][e] = 0.f;
 
         auto consume = [&](int it, const Pre& pre) {
             const int s = it % kStages;
@@ -221,22 +230,23 @@ skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
 
             // ---- B fragments: permute this thread's quarter of x into LOP3 pair order.  sum(x) over the group
             //      for tokens (2t, 2t+1) = one more MMA chain against an all-ones A fragment (exact: 1.0 * x)
-            uint32_t bfrag[P];
-            float xs0, xs1;
-            {
-                const uint32_t* n32 = reinterpret_cast<const uint32_t*>(pre.xn);  // n32[i] = codes (2i, 2i+1)
+            uint32_t bfrag[NT][P];
+            float xs0[NT], xs1[NT];
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++) {
+                const uint32_t* n32 = reinterpret_cast<const uint32_t*>(pre.xn[nt]);  // n32[i] = codes (2i, 2i+1)
 #pragma unroll
                 for (int q = 0; q < P; q++) {
                     const int ia = pair_a<BITS>(q), ib = pair_b<BITS>(q);
                     const uint32_t sel = ((ia & 1) ? 0x32u : 0x10u) | (((ib & 1) ? 0x76u : 0x54u) << 8);
-                    bfrag[q] = __byte_perm(n32[ia >> 1], n32[ib >> 1], sel);
+                    bfrag[nt][q] = __byte_perm(n32[ia >> 1], n32[ib >> 1], sel);
                 }
                 float d1[4] = {0.f, 0.f, 0.f, 0.f};
                 constexpr uint32_t kOnes = 0x3F803F80u;
 #pragma unroll
-                for (int st = 0; st < S; st++) mma16816(d1, kOnes, kOnes, kOnes, kOnes, bfrag[2 * st], bfrag[2 * st + 1]);
-                xs0 = d1[0];
-                xs1 = d1[1];
+                for (int st = 0; st < S; st++) mma16816(d1, kOnes, kOnes, kOnes, kOnes, bfrag[nt][2 * st], bfrag[nt][2 * st + 1]);
+                xs0[nt] = d1[0];
+                xs1[nt] = d1[1];
             }
 
             mbar_wait(&full_bar[s], phase);
@@ -275,7 +285,11 @@ skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
                                 wh[4 * v] = b.x; wh[4 * v + 1] = b.y; wh[4 * v + 2] = b.z; wh[4 * v + 3] = b.w;
                             }
                         }
-                        float d[4] = {0.f, 0.f, 0.f, 0.f};
+                        float d[NT][4];
+#pragma unroll
+                        for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+                            for (int e = 0; e < 4; e++) d[nt][e] = 0.f;
 #pragma unroll
                         for (int st = 0; st < S; st++) {
                             // pairs 2st, 2st+1 of the quarter -> (a0,a1) and (a2,a3)
@@ -299,9 +313,12 @@ skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
                                     ah2b[e] = lop3_and_or(wh[wi] >> sh, 0x00800080u, kMagic);
                                 }
                             }
-                            mma16816(d, al2[0], ah2[0], al2[1], ah2[1], bfrag[2 * st], bfrag[2 * st + 1]);
-                            if constexpr (BITS == 8)
-                                mma16816(d, al2b[0], ah2b[0], al2b[1], ah2b[1], bfrag[2 * st], bfrag[2 * st + 1]);
+#pragma unroll
+                            for (int nt = 0; nt < NT; nt++) {
+                                mma16816(d[nt], al2[0], ah2[0], al2[1], ah2[1], bfrag[nt][2 * st], bfrag[nt][2 * st + 1]);
+                                if constexpr (BITS == 8)
+                                    mma16816(d[nt], al2b[0], ah2b[0], al2b[1], ah2b[1], bfrag[nt][2 * st], bfrag[nt][2 * st + 1]);
+                            }
                         }
                         uint32_t s0, s1, b0, b1;
                         if constexpr (SB_TMA) {
@@ -317,10 +334,13 @@ skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
                         const float sl = __uint_as_float(s0 << 16), sh_ = __uint_as_float(s1 << 16);
                         const float cl = fmaf(-OFF, sl, __uint_as_float(b0 << 16));
                         const float ch = fmaf(-OFF, sh_, __uint_as_float(b1 << 16));
-                        yacc[q][0] = fmaf(sl, d[0], fmaf(cl, xs0, yacc[q][0]));
-                        yacc[q][1] = fmaf(sl, d[1], fmaf(cl, xs1, yacc[q][1]));
-                        yacc[q][2] = fmaf(sh_, d[2], fmaf(ch, xs0, yacc[q][2]));
-                        yacc[q][3] = fmaf(sh_, d[3], fmaf(ch, xs1, yacc[q][3]));
+#pragma unroll
+                        for (int nt = 0; nt < NT; nt++) {
+                            yacc[nt][q][0] = fmaf(sl, d[nt][0], fmaf(cl, xs0[nt], yacc[nt][q][0]));
+                            yacc[nt][q][1] = fmaf(sl, d[nt][1], fmaf(cl, xs1[nt], yacc[nt][q][1]));
+                            yacc[nt][q][2] = fmaf(sh_, d[nt][2], fmaf(ch, xs0[nt], yacc[nt][q][2]));
+                            yacc[nt][q][3] = fmaf(sh_, d[nt][3], fmaf(ch, xs1[nt], yacc[nt][q][3]));
+                        }
                     }
                 }
             }
@@ -329,16 +349,19 @@ skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
 
             if (kt == p.n_kt - 1) {
                 // ---- row-block done: 16 per-warp partials -> shared memory -> fixed-order sum -> y
-                float* mine = red + (size_t)warp * (p.rs * 8);
+                float* mine = red + (size_t)warp * (p.rs * 8 * NT);
 #pragma unroll
                 for (int q = 0; q < RT; q++) {
-                    if (q < nrt) {
-                        const int rl = 16 * q + g;
-                        *reinterpret_cast<float2*>(mine + rl * 8 + 2 * t) = make_float2(yacc[q][0], yacc[q][1]);
-                        *reinterpret_cast<float2*>(mine + (rl + 8) * 8 + 2 * t) = make_float2(yacc[q][2], yacc[q][3]);
-                    }
 #pragma unroll
-                    for (int e = 0; e < 4; e++) yacc[q][e] = 0.f;
+                    for (int nt = 0; nt < NT; nt++) {
+                        if (q < nrt) {
+                            const int rl = 16 * q + g;
+                            *reinterpret_cast<float2*>(mine + rl * (8 * NT) + 8 * nt + 2 * t) = make_float2(yacc[nt][q][0], yacc[nt][q][1]);
+                            *reinterpret_cast<float2*>(mine + (rl + 8) * (8 * NT) + 8 * nt + 2 * t) = make_float2(yacc[nt][q][2], yacc[nt][q][3]);
+                        }
+#pragma unroll
+                        for (int e = 0; e < 4; e++) yacc[nt][q][e] = 0.f;
+                    }
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kWarps * 32) : "memory");
                 const int ctid = threadIdx.x;
@@ -346,7 +369,7 @@ skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
                     const int m = i / nr, r = i - m * nr;
                     float tot = 0.f;
 #pragma unroll
-                    for (int w2 = 0; w2 < kWarps; w2++) tot += red[(size_t)w2 * (p.rs * 8) + r * 8 + m];
+                    for (int w2 = 0; w2 < kWarps; w2++) tot += red[(size_t)w2 * (p.rs * 8 * NT) + r * (8 * NT) + m];
                     float v = __bfloat162float(__float2bfloat16_rn(tot));
                     if (p.bias != nullptr) v = __fadd_rn(v, __bfloat162float(p.bias[r0 + ra + r]));
                     p.y[(size_t)m * p.N + r0 + ra + r] = __float2bfloat16_rn(v);
@@ -376,7 +399,7 @@ struct Plan {
     size_t smem;
 };
 
-Plan make_plan(int64_t N, int64_t K, int bits, int gs) {
+Plan make_plan(int64_t N, int64_t K, int bits, int gs, int nt = 1) {
     Plan pl{};
     if (!(bits == 2 || bits == 4 || bits == 8)) return pl;
     if ((gs * bits) % 128) return pl;
@@ -398,19 +421,19 @@ Plan make_plan(int64_t N, int64_t K, int bits, int gs) {
     pl.sb_tma = (G * 2) % 16 == 0;  // TMA needs a 16-byte row pitch for the scale / bias matrices
     pl.sb_off = (uint32_t)rs * pl.piece;
     pl.slot = pl.sb_off + 2u * (uint32_t)rs * 32u;  // multiple of 1024: every slot keeps the swizzle alignment
-    pl.smem = (size_t)kStages * pl.slot + 2 * kStages * 8 + (size_t)kWarps * rs * 8 * 4 + 16 + 1024;
+    pl.smem = (size_t)kStages * pl.slot + 2 * kStages * 8 + (size_t)kWarps * rs * 8 * 4 * nt + 16 + 1024;
     if (pl.smem > 227 * 1024) return pl;
     (void)N;
     pl.ok = true;
     return pl;
 }
 
-template <int BITS, int QW, bool SB_TMA>
-int launch_inst2(const CUtensorMap& tw, const CUtensorMap& ts, const CUtensorMap& tb, const SkinnyParams& p, size_t smem, int grid,
+template <int BITS, int QW, bool SB_TMA, int NT>
+int launch_inst3(const CUtensorMap& tw, const CUtensorMap& ts, const CUtensorMap& tb, const SkinnyParams& p, size_t smem, int grid,
                  cudaStream_t st) {
     static DeviceOnce configured;  // per device: the attribute is a per-device property
     if (configured.need()) {
-        cudaError_t e = cudaFuncSetAttribute(skinny_kernel<BITS, QW, SB_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(skinny_kernel<BITS, QW, SB_TMA, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return check_cuda(e);
         configured.done();
     }
@@ -424,9 +447,16 @@ int launch_inst2(const CUtensorMap& tw, const CUtensorMap& ts, const CUtensorMap
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = mmv_get_pdl_mode() > 0 ? 1 : 0;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, skinny_kernel<BITS, QW, SB_TMA>, tw, ts, tb, p);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, skinny_kernel<BITS, QW, SB_TMA, NT>, tw, ts, tb, p);
     count_launch();
     return check_cuda(e);
+}
+
+template <int BITS, int QW, bool SB_TMA>
+int launch_inst2(const CUtensorMap& tw, const CUtensorMap& ts, const CUtensorMap& tb, const SkinnyParams& p, size_t smem, int grid,
+                 cudaStream_t st) {
+    return p.M > 8 ? launch_inst3<BITS, QW, SB_TMA, 2>(tw, ts, tb, p, smem, grid, st)
+                   : launch_inst3<BITS, QW, SB_TMA, 1>(tw, ts, tb, p, smem, grid, st);
 }
 
 template <int BITS, int QW>
@@ -483,20 +513,26 @@ int launch_skinny(const void* x, const uint32_t* w, const void* s, const void* b
     }
     int grid = device_sm_count();
     if (grid > N) grid = (int)N;
-    for (int64_t m0 = 0; m0 < M; m0 += 8) {
+    // 16 tokens per pass when more than 8 remain and the 16-token reduction buffer fits (else octets)
+    const Plan pl2 = make_plan(N, K, bits, gs, 2);
+    for (int64_t m0 = 0; m0 < M;) {
+        const int64_t left = M - m0;
+        const int take = (left > 8 && pl2.ok) ? (int)(left < 16 ? left : 16) : (int)(left < 8 ? left : 8);
         p.x = reinterpret_cast<const __nv_bfloat16*>(x) + m0 * K;
         p.y = reinterpret_cast<__nv_bfloat16*>(y) + m0 * N;
-        p.M = (int)((M - m0) < 8 ? (M - m0) : 8);
+        p.M = take;
+        const size_t smem_now = take > 8 ? pl2.smem : pl.smem;
+        m0 += take;
         int rc = GBXQ_EUNSUPPORTED;
         switch (bits * 16 + pl.qw) {
-            case 4 * 16 + 1: rc = launch_inst<4, 1>(sb_tma, tw, ts, tb, p, pl.smem, grid, st); break;
-            case 4 * 16 + 2: rc = launch_inst<4, 2>(sb_tma, tw, ts, tb, p, pl.smem, grid, st); break;
-            case 4 * 16 + 4: rc = launch_inst<4, 4>(sb_tma, tw, ts, tb, p, pl.smem, grid, st); break;
-            case 2 * 16 + 1: rc = launch_inst<2, 1>(sb_tma, tw, ts, tb, p, pl.smem, grid, st); break;
-            case 2 * 16 + 2: rc = launch_inst<2, 2>(sb_tma, tw, ts, tb, p, pl.smem, grid, st); break;
-            case 8 * 16 + 2: rc = launch_inst<8, 2>(sb_tma, tw, ts, tb, p, pl.smem, grid, st); break;
-            case 8 * 16 + 4: rc = launch_inst<8, 4>(sb_tma, tw, ts, tb, p, pl.smem, grid, st); break;
-            case 8 * 16 + 8: rc = launch_inst<8, 8>(sb_tma, tw, ts, tb, p, pl.smem, grid, st); break;
+            case 4 * 16 + 1: rc = launch_inst<4, 1>(sb_tma, tw, ts, tb, p, smem_now, grid, st); break;
+            case 4 * 16 + 2: rc = launch_inst<4, 2>(sb_tma, tw, ts, tb, p, smem_now, grid, st); break;
+            case 4 * 16 + 4: rc = launch_inst<4, 4>(sb_tma, tw, ts, tb, p, smem_now, grid, st); break;
+            case 2 * 16 + 1: rc = launch_inst<2, 1>(sb_tma, tw, ts, tb, p, smem_now, grid, st); break;
+            case 2 * 16 + 2: rc = launch_inst<2, 2>(sb_tma, tw, ts, tb, p, smem_now, grid, st); break;
+            case 8 * 16 + 2: rc = launch_inst<8, 2>(sb_tma, tw, ts, tb, p, smem_now, grid, st); break;
+            case 8 * 16 + 4: rc = launch_inst<8, 4>(sb_tma, tw, ts, tb, p, smem_now, grid, st); break;
+            case 8 * 16 + 8: rc = launch_inst<8, 8>(sb_tma, tw, ts, tb, p, smem_now, grid, st); break;
         }
         if (rc != GBXQ_OK) return rc;
     }

@@ -100,7 +100,7 @@ def test_qmm_vs_oracle_small(cuda_device, kernel, bits, gs):
         with pytest.raises(RuntimeError):  # forcing a kernel that cannot serve the arguments is an error, not a fallback
             _run_case(g, cuda_device, kernel, bits, gs, 1, 70, 1024, seed=1)
         return
-    for M in (1, 2, 3) + ((8, 9) if kernel == "skinny" else ()):
+    for M in (1, 2, 3) + ((8, 9, 13, 16, 17) if kernel == "skinny" else ()):  # 9..16: one 16-token pass; 17: 16 + 1
         _run_case(g, cuda_device, kernel, bits, gs, M, 70, 1024, seed=bits * 31 + gs + M)
 
 
