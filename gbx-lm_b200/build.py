@@ -27,6 +27,7 @@ SOURCES = [
     "gbxq_mmv8_grouped.cu",
     "gbxq_stream.cu",
     "gbxq_glue.cu",
+    "gbxq_head.cu",
     "gbxq_gemm_sm100.cu",
     "gbxq_allreduce.cu",
 ]

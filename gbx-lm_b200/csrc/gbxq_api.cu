@@ -102,7 +102,12 @@ int gbxq_get_option(int key) {
     return GBXQ_EUNSUPPORTED;
 }
 
-size_t gbxq_workspace_bytes(int64_t, int64_t, int64_t, int, int, int) { return 0; }
+size_t gbxq_workspace_bytes(int64_t M, int64_t N, int64_t K, int bits, int group_size, int dtype) {
+    // only the split-K path of the tensor-core GEMM (17..256 rows of x on a layer with few output tiles) uses scratch
+    if (validate(M, N, K, bits, group_size, dtype) != GBXQ_OK || dtype != GBXQ_BF16) return 0;
+    if (select(M, N, K, bits, group_size, dtype, (const void*)16, (const void*)16, (const void*)16) != GBXQ_KERNEL_GEMM) return 0;
+    return gemm_workspace_bytes(M, N, K);
+}
 
 int gbxq_select_kernel(int64_t M, int64_t N, int64_t K, int bits, int group_size, int dtype) {
     const int rc = validate(M, N, K, bits, group_size, dtype);
@@ -114,8 +119,6 @@ int gbxq_select_kernel(int64_t M, int64_t N, int64_t K, int bits, int group_size
 int gbxq_qmm_ex(const void* x, const uint32_t* qweight, const void* scales, const void* biases, const void* bias,
                 void* y, int64_t M, int64_t N, int64_t K, int bits, int group_size, int dtype, int kernel,
                 void* workspace, size_t workspace_bytes, void* stream) {
-    (void)workspace;
-    (void)workspace_bytes;
     const int rc = validate(M, N, K, bits, group_size, dtype);
     if (rc != GBXQ_OK) return rc;
     if (M == 0 || N == 0) return GBXQ_OK;
@@ -144,7 +147,7 @@ int gbxq_qmm_ex(const void* x, const uint32_t* qweight, const void* scales, cons
             return launch_mmv(x, qweight, scales, biases, bias, y, M, N, K, bits, group_size, st);
         case GBXQ_KERNEL_GEMM:
             if (!gemm_supported(M, N, K, bits, group_size, dtype, x, qweight, y)) return GBXQ_EUNSUPPORTED;
-            return launch_gemm(x, qweight, scales, biases, bias, y, M, N, K, bits, group_size, st);
+            return launch_gemm(x, qweight, scales, biases, bias, y, M, N, K, bits, group_size, workspace, workspace_bytes, st);
     }
     return GBXQ_EUNSUPPORTED;
 }
@@ -199,6 +202,14 @@ int gbxq_qmm_grouped(const gbxq_segment* segs, int nseg, const void* x, int64_t 
         if (rc != GBXQ_OK) return rc;
     }
     return GBXQ_OK;
+}
+
+int gbxq_head_gemv(const void* x, const void* weight, void* y, int64_t M, int64_t V, int64_t K, int dtype, void* stream) {
+    if (dtype != GBXQ_BF16) return GBXQ_EUNSUPPORTED;
+    if (M < 0 || V < 0 || K <= 0) return GBXQ_ESHAPE;
+    if (M == 0 || V == 0) return GBXQ_OK;
+    if (!x || !weight || !y) return GBXQ_ENULL;
+    return launch_head_gemv(x, weight, y, M, V, K, (cudaStream_t)stream);
 }
 
 int gbxq_stream_plan(const gbxq_stream_call* calls_host, int ncalls, int64_t M, int dtype, void* host_blob,

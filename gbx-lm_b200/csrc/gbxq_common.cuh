@@ -203,12 +203,14 @@ int launch_decode_attention(const void* q, const void* kc, const void* vc, const
 int launch_add_rmsnorm(const void* x, const void* r, const void* w, float eps, void* h_out, void* y_out, int64_t rows, int H,
                        cudaStream_t st);
 int launch_silu_mul(const void* g, const void* u, void* out, int64_t n, cudaStream_t st);
+int launch_head_gemv(const void* x, const void* w, void* y, int64_t M, int64_t V, int64_t K, cudaStream_t st);
 void mmv_set_pdl_mode(int mode);
 int mmv_get_pdl_mode();
 bool gemm_supported(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype, const void* x, const void* w,
                     const void* y);
 int launch_gemm(const void* x, const uint32_t* w, const void* s, const void* b, const void* bias, void* y, int64_t M,
-                int64_t N, int64_t K, int bits, int gs, cudaStream_t st);
+                int64_t N, int64_t K, int bits, int gs, void* workspace, size_t workspace_bytes, cudaStream_t st);
+size_t gemm_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int launch_allreduce_oneshot(const void* in, void* out, int64_t count, int dtype, void* const* peer_bufs,
                              uint32_t* const* peer_flags, int64_t capacity, int rank, int world, uint32_t seq,
                              cudaStream_t st);

@@ -124,6 +124,12 @@ struct GemmParams {
     __nv_bfloat16* y;
     int64_t M, N, K;
     int gs_shift;
+    // split-K (skinny batches: 17..256 tokens leave only N/128 output tiles, a fraction of the 148 SMs): blockIdx.z
+    // owns k-blocks [z*kb_per_split, ...), writes its fp32 partial tile to `ws` [splits][M][N]; the CTA that arrives
+    // last at the tile's counter adds the partials in split order (deterministic) and rounds once to bf16.
+    int splits, kb_per_split;  // kb_per_split is a multiple of 16 k-blocks (whole weight pairs and scale slots)
+    float* ws;
+    uint32_t* cnt;             // one counter per output tile, zero before and after the launch
 };
 
 // The 16 (3-bit: 32) consecutive codes of one row a dequant thread owns per k-block + the raw bf16
@@ -243,10 +249,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
     const int lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * kTileN;
     const int m0 = blockIdx.y * BN;
-    const int nkb = (int)(p.K / kBlockK);
+    const int nkb_all = (int)(p.K / kBlockK);
+    const int kb_lo = p.splits > 1 ? (int)blockIdx.z * p.kb_per_split : 0;   // first k-block of this split
+    const int nkb = p.splits > 1 ? min(p.kb_per_split, nkb_all - kb_lo) : nkb_all;  // k-blocks of this CTA (loops are local)
+    const int pr_lo = kb_lo >> 1;
     const int npair = (nkb + 1) >> 1;                     // packed-weight slots: 2 k-blocks each
     const int kb_per_s = p.gs_shift == 5 ? 4 : (p.gs_shift == 6 ? 8 : 16);  // k-blocks per scale slot (8 groups)
     const int nsl = (nkb + kb_per_s - 1) / kb_per_s;
+    const int sl_lo = kb_lo / kb_per_s;
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -285,14 +295,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                 const int s = pr % WS;
                 mbar_wait(&wempty[s], ((uint32_t)(pr / WS) & 1u) ^ 1u);
                 mbar_arrive_expect_tx(&wfull[s], C::W_SLOT);
-                tma_load_2d(wring + (size_t)s * C::W_SLOT, &tmap_w, pr * 4 * BITS, n0, &wfull[s]);
+                tma_load_2d(wring + (size_t)s * C::W_SLOT, &tmap_w, (pr_lo + pr) * 4 * BITS, n0, &wfull[s]);
             };
             auto issue_s = [&](int sl) {  // scales + biases of groups 8sl .. 8sl+7
                 const int s = sl % SS;
                 mbar_wait(&sempty[s], ((uint32_t)(sl / SS) & 1u) ^ 1u);
                 mbar_arrive_expect_tx(&sfull[s], C::S_SLOT);
-                tma_load_2d(sring + (size_t)s * C::S_SLOT, &tmap_s, sl * 8, n0, &sfull[s]);
-                tma_load_2d(sring + (size_t)s * C::S_SLOT + kTileN * 16, &tmap_b, sl * 8, n0, &sfull[s]);
+                tma_load_2d(sring + (size_t)s * C::S_SLOT, &tmap_s, (sl_lo + sl) * 8, n0, &sfull[s]);
+                tma_load_2d(sring + (size_t)s * C::S_SLOT + kTileN * 16, &tmap_b, (sl_lo + sl) * 8, n0, &sfull[s]);
             };
             // run the small streams ahead of the x stream: WS-1 weight slots and one scale slot in flight
             issue_s(0);
@@ -303,7 +313,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                 const int s = kb % XS;
                 mbar_wait(&empty_b[s], ((uint32_t)(kb / XS) & 1u) ^ 1u);
                 mbar_arrive_expect_tx(&full_b[s], C::B_BYTES);
-                tma_load_2d(xring + (size_t)s * C::B_BYTES, &tmap_x, kb * kBlockK, m0, &full_b[s]);
+                tma_load_2d(xring + (size_t)s * C::B_BYTES, &tmap_x, (kb_lo + kb) * kBlockK, m0, &full_b[s]);
             }
         }
     } else if (warp == 1 + kDequantWarps) {
@@ -406,14 +416,43 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                 for (int j = 0; j < STEP; j++) {
                     const int64_t m = (int64_t)m0 + c0 + j;
                     if (m < p.M) {
-                        float f = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[j])));
-                        if (p.bias != nullptr) f = __fadd_rn(f, bias_f);
-                        p.y[(size_t)m * p.N + n] = __float2bfloat16_rn(f);
+                        if (p.splits > 1) {
+                            p.ws[((size_t)blockIdx.z * p.M + m) * p.N + n] = __uint_as_float(v[j]);
+                        } else {
+                            float f = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[j])));
+                            if (p.bias != nullptr) f = __fadd_rn(f, bias_f);
+                            p.y[(size_t)m * p.N + n] = __float2bfloat16_rn(f);
+                        }
                     }
                 }
             }
         }
         tc_fence_before();
+        if (p.splits > 1) {
+            // the last split to arrive at this tile's counter adds the partial tiles in split order and writes y
+            __threadfence();
+            asm volatile("bar.sync 2, %0;" ::"n"(kDequantWarps * 32) : "memory");
+            uint32_t* flag = tmem_slot + 1;  // shared scratch next to the TMEM address
+            const uint32_t tile = blockIdx.y * gridDim.x + blockIdx.x;
+            if (warp == 1 && lane == 0) *flag = atomicAdd(p.cnt + tile, 1u) == (uint32_t)p.splits - 1u ? 1u : 0u;
+            asm volatile("bar.sync 2, %0;" ::"n"(kDequantWarps * 32) : "memory");
+            if (*flag != 0u) {
+                __threadfence();
+                if (row_ok) {
+                    for (int c = cq * QCOLS; c < (cq + 1) * QCOLS; c++) {
+                        const int64_t m = (int64_t)m0 + c;
+                        if (m < p.M) {
+                            float acc = 0.f;
+                            for (int z = 0; z < p.splits; z++) acc += __ldcg(p.ws + ((size_t)z * p.M + m) * p.N + n);
+                            float f = __bfloat162float(__float2bfloat16_rn(acc));
+                            if (p.bias != nullptr) f = __fadd_rn(f, bias_f);
+                            p.y[(size_t)m * p.N + n] = __float2bfloat16_rn(f);
+                        }
+                    }
+                }
+                if (warp == 1 && lane == 0) p.cnt[tile] = 0u;  // left zero for the next launch
+            }
+        }
     }
     __syncthreads();
     if (warp == 0) {
@@ -467,7 +506,7 @@ int launch_inst(const Maps& mp, const GemmParams& p, cudaStream_t st) {
         if (e != cudaSuccess) return check_cuda(e);
         configured.done();
     }
-    dim3 grid((unsigned)((p.N + kTileN - 1) / kTileN), (unsigned)((p.M + BN - 1) / BN));
+    dim3 grid((unsigned)((p.N + kTileN - 1) / kTileN), (unsigned)((p.M + BN - 1) / BN), (unsigned)(p.splits > 1 ? p.splits : 1));
     gemm_kernel<BITS, BN><<<grid, kThreads, smem, st>>>(mp.x, mp.w, mp.s, mp.b, p);
     count_launch();
     return check_cuda(cudaGetLastError());
@@ -508,8 +547,40 @@ bool gemm_supported(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype
     return get_encode() != nullptr;
 }
 
+// Split-K plan for a skinny batch: how many splits, k-blocks per split, workspace bytes (counter header + partials).
+constexpr size_t kCntBytes = 16384;  // up to 4096 output tiles
+void gemm_split_plan(int64_t M, int64_t N, int64_t K, int* splits, int* kb_per_split, size_t* ws_bytes) {
+    *splits = 1;
+    *kb_per_split = 0;
+    *ws_bytes = 0;
+    if (M > 256 || M < 1) return;
+    const int bn = pick_bn(M);
+    const int64_t tiles = ((N + kTileN - 1) / kTileN) * ((M + bn - 1) / bn);
+    const int64_t nkb = K / kBlockK;
+    const int sms = device_sm_count();
+    if (tiles * 2 > sms || tiles > 4096) return;      // enough CTAs already
+    int want = (int)(sms / tiles);
+    if (want > 8) want = 8;
+    const int chunks = (int)((nkb + 15) / 16);         // splits are whole 16-k-block chunks (weight pairs, scale slots)
+    if (want > chunks) want = chunks;
+    if (want < 2) return;
+    const int per = (chunks + want - 1) / want * 16;
+    const int s = (int)((nkb + per - 1) / per);
+    if (s < 2) return;
+    *splits = s;
+    *kb_per_split = per;
+    *ws_bytes = kCntBytes + (size_t)s * (size_t)M * (size_t)N * 4;
+}
+
+size_t gemm_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+    int s, per;
+    size_t b;
+    gemm_split_plan(M, N, K, &s, &per, &b);
+    return b;
+}
+
 int launch_gemm(const void* x, const uint32_t* w, const void* s, const void* b, const void* bias, void* y, int64_t M,
-                int64_t N, int64_t K, int bits, int gs, cudaStream_t st) {
+                int64_t N, int64_t K, int bits, int gs, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     if (get_encode() == nullptr) return GBXQ_EUNSUPPORTED;
     if (((uintptr_t)s | (uintptr_t)b) & 15) return GBXQ_EUNSUPPORTED;
     const int bn = pick_bn(M);
@@ -530,6 +601,18 @@ int launch_gemm(const void* x, const uint32_t* w, const void* s, const void* b, 
     p.N = N;
     p.K = K;
     p.gs_shift = gs == 32 ? 5 : (gs == 64 ? 6 : 7);
+    p.splits = 1;
+    {
+        int sp, per;
+        size_t need;
+        gemm_split_plan(M, N, K, &sp, &per, &need);
+        if (sp > 1 && workspace != nullptr && workspace_bytes >= need && !((uintptr_t)workspace & 15)) {
+            p.splits = sp;
+            p.kb_per_split = per;
+            p.cnt = reinterpret_cast<uint32_t*>(workspace);
+            p.ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + kCntBytes);
+        }
+    }
     switch (bits) {
         case 2: return launch_bn<2>(bn, mp, p, st);
         case 3: return launch_bn<3>(bn, mp, p, st);

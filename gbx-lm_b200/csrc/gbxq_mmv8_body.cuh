@@ -157,6 +157,7 @@ struct Mmv8Params {
     uint32_t slot_bytes;  // ring slot size
     uint32_t sb_off;      // offset of the scales inside a slot (biases follow at sb_off + tr*G*2)
     int early_weights;    // 1: weights are immutable while the call is in flight -> stream them before griddepcontrol.wait
+    int row_unit;         // rows are shared out in units of 1 row, or of 4 rows when a row of scales is only 8-byte aligned
     unsigned long long* dbg;  // optional timeline (gbxq_debug_timeline): 8 globaltimer stamps per launch, CTA 0 / warp 0
     int dbg_all;              // 1: every CTA stamps (8 slots per CTA)
     int pre_stages;           // > 0: the producer issues only this many stages until the activations have been read
@@ -224,8 +225,8 @@ __device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, ui
 
     STAMP(0);
     const bool extra = bid < p.rows_rem;
-    const int64_t r0 = (int64_t)bid * p.rows_base + (extra ? bid : p.rows_rem);
-    const int rows = p.rows_base + (extra ? 1 : 0);
+    const int64_t r0 = (int64_t)bid * p.rows_base + (int64_t)(extra ? bid : p.rows_rem) * p.row_unit;
+    const int rows = p.rows_base + (extra ? p.row_unit : 0);
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int nstg = p.stages;
@@ -659,7 +660,7 @@ __device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, ui
 // ------------------------------------------------------------------------------------------ host side
 struct Plan {
     bool ok;
-    int mt, cpw, R, nch, cw, rg, tr, stages, grid;
+    int mt, cpw, R, nch, cw, rg, tr, stages, grid, row_unit;
     uint32_t slot_bytes, sb_off;
     size_t smem;
 };
@@ -675,7 +676,12 @@ inline Plan make_plan(int64_t M, int64_t N, int64_t K, int bits, int gs, int gri
     if (!(bits == 2 || bits == 3 || bits == 4 || bits == 6 || bits == 8) || M < 1 || M > 4 || N < 1) return pl;
     if ((bits == 2 || bits == 3 || bits == 6) && gs == 32) return pl;  // a thread chunk would be a fraction of a word
     const int64_t G = K / gs;
-    if (G % 8) return pl;  // S | G, and 16-byte rows of scales for the bulk copies
+    // S | G.  The scales / biases of a stage travel as ONE bulk copy (the rows of a stage are contiguous), which needs a
+    // 16-byte aligned start: any row when G % 8 == 0; with G % 8 == 4 (tensor-parallel K shards: Qwen2.5-32B down_proj
+    // K/2 = 13824 at gs 128) every CTA range and stage must start on an even row -> rows are shared out in units of 4
+    if (G % 4) return pl;
+    pl.row_unit = (G % 8) ? 4 : 1;
+    if (pl.row_unit == 4 && (N % 4)) return pl;
     const int64_t row_bytes = K * bits / 8;
     pl.mt = M == 1 ? 1 : (M == 2 ? 2 : 4);
     pl.nch = (int)(G / S);
@@ -708,7 +714,7 @@ inline Plan make_plan(int64_t M, int64_t N, int64_t K, int bits, int gs, int gri
     if ((int64_t)grid * min_rows > N) grid = (int)((N + min_rows - 1) / min_rows);
     if (grid < 1) grid = 1;
     pl.grid = grid;
-    const int64_t rows_max = (N + grid - 1) / grid;
+    const int64_t rows_max = ((N / pl.row_unit + grid - 1) / grid) * pl.row_unit;
     pl.smem = (size_t)pl.stages * pl.slot_bytes + 2 * kMaxStages * 8 + (size_t)kCW * pl.cpw * S * pl.mt * 4 +
               (size_t)rows_max * 2 * pl.cw * pl.mt * 4 + 16;
     if (pl.smem > 110 * 1024) return pl;
@@ -754,15 +760,16 @@ inline Mmv8Params make_params(const Plan& pl, const void* x, const uint32_t* w, 
     p.early_weights = early;
     static const int pre_stages = env_int("GBXQ_MMV8_PRE_STAGES", 2);
     p.pre_stages = pre_stages;
-    p.rows_base = (int)(N / pl.grid);
-    p.rows_rem = (int)(N % pl.grid);
+    p.row_unit = pl.row_unit;
+    p.rows_base = (int)((N / pl.row_unit) / pl.grid) * pl.row_unit;
+    p.rows_rem = (int)((N / pl.row_unit) % pl.grid);
     auto spr_of = [&](int rows) {
         if (rows <= 0) return W;
         const int ns = (rows + pl.tr - 1) / pl.tr;
         return (((rows + ns - 1) / ns + W - 1) / W) * W;  // balanced stages, whole MMA sets
     };
     p.spr0 = spr_of(p.rows_base);
-    p.spr1 = spr_of(p.rows_base + 1);
+    p.spr1 = spr_of(p.rows_base + pl.row_unit);
     return p;
 }
 

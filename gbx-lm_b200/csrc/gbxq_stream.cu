@@ -131,8 +131,8 @@ __global__ void __launch_bounds__(kThreads, kMinCtas)
                 if (sg < 0) continue;
                 const Mmv8Params& q = d->seg[sg];
                 const bool extra = lbid < q.rows_rem;
-                const int rows = q.rows_base + (extra ? 1 : 0);
-                const int64_t r0 = (int64_t)lbid * q.rows_base + (extra ? lbid : q.rows_rem);
+                const int rows = q.rows_base + (extra ? q.row_unit : 0);
+                const int64_t r0 = (int64_t)lbid * q.rows_base + (int64_t)(extra ? lbid : q.rows_rem) * q.row_unit;
                 const int spr = extra ? q.spr1 : q.spr0;
                 const uint32_t row_bytes = q.row_bytes, g2 = (uint32_t)q.G * 2u, sb_off = q.sb_off;
                 const uint32_t bi_off = sb_off + (uint32_t)q.tr * g2;
@@ -294,7 +294,7 @@ int stream_plan(const gbxq_stream_call* calls, int ncalls, int64_t M, int dtype,
             if (i > 0 && (pl.cpw != first.cpw || pl.R != first.R)) return GBXQ_EUNSUPPORTED;
             plans[(size_t)c * GBXQ_MAX_SEGMENTS + i].pl = pl;
             if (pl.slot_bytes > slot_max) slot_max = pl.slot_bytes;
-            const int64_t rows_max = (sg.N + pl.grid - 1) / pl.grid;
+            const int64_t rows_max = ((sg.N / pl.row_unit + pl.grid - 1) / pl.grid) * pl.row_unit;
             const size_t tail = (size_t)kCW * pl.cpw * S * mt * 4 + (size_t)rows_max * 2 * pl.cw * mt * 4 + 16;
             if (tail > tail_max) tail_max = tail;
         }

@@ -75,6 +75,24 @@ def _check_shapes(w, scales, biases, group_size: int, bits: int, k_x: Optional[i
     return n, k
 
 
+_WORKSPACES: dict = {}
+
+
+def _workspace(device: torch.device, stream: int, m: int, n: int, k: int, bits: int, group_size: int, dt: int):
+    """Scratch for the split-K path of the tensor-core GEMM (gbxq_workspace_bytes): one zero-initialised buffer per
+    (device, stream), grown on demand and reused by every call of that stream (calls of one stream are ordered; the kernel
+    leaves the counter header zero)."""
+    need = int(_lib.get().gbxq_workspace_bytes(m, n, k, bits, group_size, dt))
+    if need == 0:
+        return None, 0
+    key = (device.index, stream)
+    buf = _WORKSPACES.get(key)
+    if buf is None or buf.numel() < need:
+        buf = torch.zeros((max(need, 8 << 20),), dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = buf
+    return buf, buf.numel()
+
+
 def _qmm_impl(x, w, scales, biases, bias, group_size: int, bits: int, kernel: int) -> torch.Tensor:
     _require_cuda(x, w, scales, biases, bias)
     _as_u32_ptr_tensor(w)
@@ -100,10 +118,11 @@ def _qmm_impl(x, w, scales, biases, bias, group_size: int, bits: int, kernel: in
     y = torch.empty((m, n), dtype=x.dtype, device=x.device)
     with torch.cuda.device(x.device):
         st = torch.cuda.current_stream().cuda_stream
+        ws, ws_bytes = _workspace(x.device, st, m, n, k, bits, group_size, dt) if m > 16 else (None, 0)
         rc = _lib.get().gbxq_qmm_ex(
             x2.data_ptr(), w.data_ptr(), scales.data_ptr(), biases.data_ptr(),
             bias.data_ptr() if bias is not None else None, y.data_ptr(),
-            m, n, k, bits, group_size, dt, kernel, None, 0, st,
+            m, n, k, bits, group_size, dt, kernel, ws.data_ptr() if ws is not None else None, ws_bytes, st,
         )
     _lib.check(rc, "gbxq_qmm")
     return y.reshape(*lead, n)
@@ -413,6 +432,27 @@ def silu_mul(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
         rc = _lib.get().gbxq_silu_mul(gate.data_ptr(), up.data_ptr(), out.data_ptr(), gate.numel(), _stream())
     _lib.check(rc, "gbxq_silu_mul")
     return out
+
+
+def head_linear(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """logits = x . weight^T with the UNQUANTIZED bf16 vocabulary matrix (`lm_head` / `embed_tokens.as_linear`,
+    gbx_lm/models/qllama.py:183-184,194-198).  Decode-sized inputs (<= 8 rows) stream through gbxq_head_gemv; anything
+    else (prefill, other dtypes) is the framework's dense matmul."""
+    k = x.shape[-1]
+    rows = x.numel() // k
+    if (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and weight.is_contiguous()
+            and 1 <= rows <= 8 and k % 256 == 0 and k * max(rows, 1) * 2 <= 100 * 1024):
+        x2 = x.reshape(rows, k)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        v = weight.shape[0]
+        y = torch.empty((rows, v), dtype=torch.bfloat16, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.get().gbxq_head_gemv(x2.data_ptr(), weight.data_ptr(), y.data_ptr(), rows, v, k, 0, _stream())
+        if rc != -9:
+            _lib.check(rc, "gbxq_head_gemv")
+            return y.reshape(*x.shape[:-1], v)
+    return torch.nn.functional.linear(x, weight)
 
 
 def dequantize(w: torch.Tensor, scales: torch.Tensor, biases: torch.Tensor, group_size: int = 64, bits: int = 4) -> torch.Tensor:

@@ -273,10 +273,10 @@ class Model(nn.Module):  # gbx_lm/models/qllama.py:177-209
                 for c in cache:
                     c.offset = off + L
         out = self.model(inputs, positions, cache, attend_len)
-        if self.args.tie_word_embeddings:
-            logits = F.linear(out, self.model.embed_tokens.weight)  # embed_tokens.as_linear
-        else:
-            logits = self.lm_head(out)
+        # vocabulary projection (qllama.py:194-198): decode-sized inputs go through the streaming bf16 GEMV
+        # (gbxq_head_gemv), prefill through the dense matmul
+        head = self.model.embed_tokens.weight if self.args.tie_word_embeddings else self.lm_head.weight
+        logits = ops.head_linear(out, head) if FUSED_DECODE else F.linear(out, head)
         return (logits, out) if hidden_states else logits
 
     def sanitize(self, weights: Dict[str, Any]) -> Dict[str, Any]:  # qllama.py:201-205

@@ -177,7 +177,10 @@ int gbxq_stream_plan(const gbxq_stream_call* calls_host, int ncalls, int64_t M, 
                      size_t blob_capacity, gbxq_stream_info* info);
 int gbxq_qmm_stream(const gbxq_stream_info* info, const void* blob_dev, void* counters_dev, void* stream);
 
-/* Scratch bytes gbxq_qmm may use for these arguments (0 today for every shipped kernel). */
+/* Scratch bytes gbxq_qmm can use for these arguments: non-zero only where the tensor-core GEMM splits K (17..256 rows of x
+ * on a layer with fewer output tiles than SMs).  The first 16 KB of the workspace must be zero before the first call
+ * and are left zero by every call; one workspace may serve all calls of a stream.  With workspace == NULL (or too
+ * small) the call runs unsplit -- same result up to fp32 summation order, fewer SMs busy. */
 size_t gbxq_workspace_bytes(int64_t M, int64_t N, int64_t K, int bits, int group_size, int dtype);
 
 /*
@@ -219,6 +222,13 @@ int gbxq_add_rmsnorm(const void* x, const void* r, const void* w, float eps, voi
                      int H, void* stream);
 int gbxq_silu_mul(const void* gate, const void* up, void* out, int64_t n, void* stream);
 
+/*
+ * Vocabulary projection of the decode step: y[M,V] = x[M,K] . weight[V,K]^T with UNQUANTIZED bf16
+ * weights -- `self.lm_head(out)` / `self.model.embed_tokens.as_linear(out)` (gbx_lm/models/qllama.py:183-184,194-198).
+ * A streaming GEMV for M <= 8 rows (K % 256 == 0, 16-byte aligned x / weight): fp32 accumulation, one rounding to bf16.
+ * Returns GBXQ_EUNSUPPORTED (nothing enqueued) for other arguments: use the framework's dense matmul then.
+ */
+int gbxq_head_gemv(const void* x, const void* weight, void* y, int64_t M, int64_t V, int64_t K, int dtype, void* stream);
 /*
  * Tensor-parallel row-parallel epilogue (new work; the reference has no TP -- SURVEY.md 2.2):
  * one-shot sum all-reduce of a small [count] T vector over peer-mapped buffers on NVLink

@@ -104,3 +104,38 @@ def test_fused_decode_matches_unfused_model(cuda_device, tmp_path, monkeypatch):
     top2 = b.topk(2, -1).values
     clear = (top2[..., 0] - top2[..., 1]) > 0.05 * b.abs().max()
     assert clear.sum() >= 10 and (a.argmax(-1)[clear] == b.argmax(-1)[clear]).all()
+
+
+@pytest.mark.parametrize("shape", [(1, 128256, 2048), (1, 128256, 4096), (4, 512, 256), (8, 1000, 3072), (2, 152064, 5120), (3, 7, 8192)])
+def test_head_gemv_matches_fp32_linear(cuda_device, shape):
+    """gbxq_head_gemv (the unquantized vocabulary projection, qllama.py:183-184,194-198) against F.linear evaluated in
+    fp32 on the same bf16 operands: one bf16 rounding of the exact sum (relative tolerance 2^-8 plus fp32 summation
+    noise), and bitwise reproducible."""
+    from gbx_lm_b200 import ops
+
+    m, v, k = shape
+    g = torch.Generator(device=cuda_device).manual_seed(m + v + k)
+    w = (torch.randn((v, k), generator=g, device=cuda_device) / k ** 0.5).to(torch.bfloat16)
+    x = torch.randn((m, k), generator=g, device=cuda_device).to(torch.bfloat16)
+    n0 = ops.launch_count()
+    y = ops.head_linear(x, w)
+    assert ops.launch_count() == n0 + 1, "the head did not go through gbxq_head_gemv"
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ref = torch.nn.functional.linear(x.float(), w.float())
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    assert y.shape == (m, v) and y.dtype == torch.bfloat16
+    err = (y.float() - ref).abs().max() / ref.abs().max()
+    assert err <= 2.0 ** -8, err
+    # where the fp32 reference is not within rounding of a bf16 tie the bf16 result is exactly the rounded reference
+    assert (y == ref.to(torch.bfloat16)).float().mean() > 0.99
+    assert torch.equal(y, ops.head_linear(x, w))
+    # 3-D input, as the model passes it
+    assert torch.equal(ops.head_linear(x[:, None, :], w)[:, 0], y)
+    # prefill-sized input falls back to the dense matmul (no gbxq launch)
+    xl = torch.randn((9, k), generator=g, device=cuda_device).to(torch.bfloat16)
+    n1 = ops.launch_count()
+    yl = ops.head_linear(xl, w)
+    assert ops.launch_count() == n1 and yl.shape == (9, v)

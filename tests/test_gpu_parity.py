@@ -127,6 +127,20 @@ def test_qmm_mmv_vs_oracle_small(cuda_device, kernel, bits, gs):
         _run_case(g, cuda_device, kernel, bits, gs, M, 70, 1024, seed=bits * 31 + gs + M, with_bias=(M == 3))
 
 
+@pytest.mark.parametrize("bits,gs,K", [(4, 128, 1536), (4, 64, 768), (2, 128, 3584), (3, 64, 1792), (8, 64, 256 + 512)])
+def test_qmm_mmv8_rows_of_scales_only_8_byte_aligned(cuda_device, bits, gs, K):
+    """K / group_size = 4 (mod 8): a row of scales is 8 bytes off the 16-byte grid the bulk copies need (the K shards of
+    tensor parallelism: Qwen2.5-32B down_proj K/2 = 13824 at gs 128, Llama-3-8B down_proj K/8 = 1792).  The kernel then
+    shares rows out in units of four; N % 4 != 0 is refused."""
+    g = _ops()
+    assert (K // gs) % 8 == 4
+    for M in (1, 2, 4):
+        for N in (72, 1028, 4):
+            _run_case(g, cuda_device, "mmv8", bits, gs, M, N, K, seed=bits + gs + M + N, with_bias=(M == 2))
+    with pytest.raises(RuntimeError):
+        _run_case(g, cuda_device, "mmv8", bits, gs, 1, 70, K, seed=1)
+
+
 def test_qmm_mmv8_block_fixed_point_ranges(cuda_device):
     """The integer kernel represents x per (token, group) as 15-bit block fixed point: check wide dynamic range inside a
     group (outlier channels), tiny and huge magnitudes, exact zeros, and that inf / nan poison only what they should."""
@@ -247,6 +261,28 @@ def test_qmm_gemm_tcgen05_vs_oracle(cuda_device, bits, gs):
     # the TMA descriptors need 16-byte row pitches: K*bits/8 and (K/gs)*2 multiples of 16
     for (M, N, K) in ((17, 128, 1024), (64, 200, 1024), (100, 384, 2048), (300, 130, 4096)):
         _run_case(g, cuda_device, "gemm", bits, gs, M, N, K, seed=bits + gs + M, with_bias=(M == 100), tol=1e-2)
+
+
+@pytest.mark.parametrize("M,N,K,bits,gs", [(32, 512, 4096, 4, 64), (64, 640, 6144, 4, 128), (17, 128, 8192, 2, 64), (256, 1024, 3072, 8, 64),
+                                          (100, 384, 5120, 3, 64)])
+def test_qmm_gemm_split_k(cuda_device, M, N, K, bits, gs):
+    """Skinny batches on layers with few output tiles: the tcgen05 GEMM splits K over blockIdx.z (fp32 partial tiles in
+    the workspace, last split to arrive reduces in split order).  Against the oracle, bitwise reproducible call after
+    call (the tile counters are left zero), and within fp32 summation noise of the unsplit launch."""
+    g = _ops()
+    from gbx_lm_b200 import _lib
+
+    assert _lib.get().gbxq_workspace_bytes(M, N, K, bits, gs, 0) > 16384, "shape does not exercise split-K"
+    L = A.synth_layer(N, K, bits, gs, seed=M + N, with_bias=True)
+    d = layer_to_cuda(L, cuda_device)
+    xb = A.synth_x(M, K, seed=K)
+    x = bf16_from_bits(xb, cuda_device)
+    ys = [g.quantized_matmul(x, d["qweight"], d["scales"], d["zeros"], True, gs, bits, bias=d["bias"], kernel="gemm") for _ in range(3)]
+    ref = A.quantized_matmul(xb, L["qweight"], L["scales"], L["zeros"], gs, bits, "bf16", "f64", bias=L["bias"])
+    assert_close_to_truth(ys[0], ref, f"gemm split-K M{M} N{N} K{K} b{bits}", 1e-2)
+    assert torch.equal(ys[0], ys[1]) and torch.equal(ys[0], ys[2])
+    # auto dispatch (M >= 17 -> GEMM) takes the same path
+    assert torch.equal(ys[0], g.quantized_matmul(x, d["qweight"], d["scales"], d["zeros"], True, gs, bits, bias=d["bias"]))
 
 
 def test_qmm_gemm_declines_unaligned_pitch(cuda_device):
