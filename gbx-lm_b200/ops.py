@@ -11,6 +11,8 @@ propagation, CUDA-graph capturable: the library only enqueues on the current str
 CUDA only -- there is deliberately no CPU implementation."""
 from __future__ import annotations
 
+import os
+
 from typing import List, Optional, Sequence
 
 import torch
@@ -83,7 +85,7 @@ def _workspace(device: torch.device, stream: int, m: int, n: int, k: int, bits: 
     (device, stream), grown on demand and reused by every call of that stream (calls of one stream are ordered; the kernel
     leaves the counter header zero)."""
     need = int(_lib.get().gbxq_workspace_bytes(m, n, k, bits, group_size, dt))
-    if need == 0:
+    if need == 0 or os.environ.get("GBXQ_NO_SPLITK") == "1":  # the switch exists for A/B measurements and tests
         return None, 0
     key = (device.index, stream)
     buf = _WORKSPACES.get(key)
@@ -434,14 +436,19 @@ def silu_mul(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
     return out
 
 
+# rows served by gbxq_head_gemv: measured (profiles/r02k_headbench.txt) 1.00-1.04 of the HBM peak at one row, as fast as the
+# dense matmul; from 4 rows on the kernel is bound by its shared-memory reads of x (0.65 / 0.38 at 4 / 8 rows)
+_HEAD_MAX_ROWS = 2
+
+
 def head_linear(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
     """logits = x . weight^T with the UNQUANTIZED bf16 vocabulary matrix (`lm_head` / `embed_tokens.as_linear`,
     gbx_lm/models/qllama.py:183-184,194-198).  Decode-sized inputs (<= 8 rows) stream through gbxq_head_gemv; anything
-    else (prefill, other dtypes) is the framework's dense matmul."""
+    else (more rows, prefill, other dtypes) is the framework's dense matmul."""
     k = x.shape[-1]
     rows = x.numel() // k
     if (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and weight.is_contiguous()
-            and 1 <= rows <= 8 and k % 256 == 0 and k * max(rows, 1) * 2 <= 100 * 1024):
+            and 1 <= rows <= _HEAD_MAX_ROWS and k % 256 == 0 and k * max(rows, 1) * 2 <= 100 * 1024):
         x2 = x.reshape(rows, k)
         if not x2.is_contiguous():
             x2 = x2.contiguous()

@@ -73,10 +73,10 @@ def quantize_affine(w: torch.Tensor, group_size: int = 64, bits: int = 4):
     q0 = torch.round(edge / scales)
     scales = torch.where(q0 != 0, edge / torch.where(q0 != 0, q0, torch.ones_like(q0)), scales)
     biases = torch.where(q0 == 0, torch.zeros_like(edge), edge)
-    scales = scales.to(dt)
-    biases = biases.to(dt)
-    q = torch.round((g - biases.float()[..., None]) / scales.float()[..., None]).clamp(0, n_bins).to(torch.uint8)
-    return pack_codes(q.reshape(n, k), bits), scales, biases
+    # the codes come from the UNROUNDED fp32 scale / bias; only the stored statistics are cast to w.dtype (the order of
+    # MLX's CPU quantize: rint((w - bias) / scale) before the static_cast of scales / biases)
+    q = torch.round((g - biases[..., None]) / scales[..., None]).clamp(0, n_bins).to(torch.uint8)
+    return pack_codes(q.reshape(n, k), bits), scales.to(dt), biases.to(dt)
 
 
 def synth_layer(n: int, k: int, bits: int, group_size: int, seed: int = 0, with_bias: bool = False,
