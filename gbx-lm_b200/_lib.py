@@ -6,10 +6,11 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgbxq.so")
+# GBXQ_LIB: development aid (A/B builds of the same library); still a CUDA build of this tree, never a fallback
+LIB_PATH = os.environ.get("GBXQ_LIB") or os.path.join(HERE, "libgbxq.so")
 
 BF16, F16, F32 = 0, 1, 2
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_GEMV, KERNEL_GEMM, KERNEL_SKINNY, KERNEL_MMV, KERNEL_MMV8 = 0, 1, 2, 3, 4, 5, 6
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_GEMV, KERNEL_GEMM, KERNEL_SKINNY, KERNEL_MMV, KERNEL_MMV8, KERNEL_GEMM_TS = 0, 1, 2, 3, 4, 5, 6, 7
 OPT_PDL = 1
 AR_MAX_CTAS = 32
 RP_MAX_CTAS = 512

@@ -29,6 +29,7 @@ SOURCES = [
     "gbxq_glue.cu",
     "gbxq_head.cu",
     "gbxq_gemm_sm100.cu",
+    "gbxq_gemm_ts_sm100.cu",
     "gbxq_allreduce.cu",
 ]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -53,7 +54,13 @@ def needs_build() -> bool:
     return not os.path.exists(LIB) or os.path.getmtime(LIB) < _deps_mtime()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, variant: str = "", extra_flags=()) -> str:
+    """variant / extra_flags: an A/B build with other -D flags into libgbxq_<variant>.so (objects kept apart)."""
+    global OBJ, LIB
+    if variant:
+        OBJ = os.path.join(CSRC, "_obj_" + variant)
+        LIB = os.path.join(HERE, f"libgbxq_{variant}.so")
+        force = True
     if not force and not needs_build():
         return LIB
     os.makedirs(OBJ, exist_ok=True)
@@ -70,7 +77,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
         if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr_time):
-            cmd = [exe, *NVCC_FLAGS, "-c", s, "-o", o]
+            cmd = [exe, *NVCC_FLAGS, *extra_flags, "-c", s, "-o", o]
             if verbose:
                 cmd.insert(1, "-Xptxas")
                 cmd.insert(2, "-v")
@@ -94,4 +101,6 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    var = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, variant=var[0] if var else "",
+                extra_flags=[a for a in sys.argv[1:] if a.startswith("-D")]))

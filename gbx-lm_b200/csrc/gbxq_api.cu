@@ -3,6 +3,7 @@
 // gbx_lm/models/quantized_linear_gba.py:195-205 (quantized_matmul + bias) and
 // gbx_lm/tuner/lora.py:62-68 (dequantize).
 #include <atomic>
+#include <cstdlib>
 
 #include "gbxq_common.cuh"
 
@@ -30,8 +31,18 @@ int device_sm_count() {
 static constexpr int64_t kMmvMaxM = 2;
 static constexpr int64_t kSkinnyMaxM = 16;  // 2 passes of 8 tokens; above that the tcgen05 GEMM amortises better
 
+// Rows of x from which the TMEM-operand GEMM (gbxq_gemm_ts_sm100.cu) takes over (GBXQ_TS_MIN_M overrides; 0 = never).
+static int ts_min_m() {
+    static const int v = [] {
+        const char* e = getenv("GBXQ_TS_MIN_M");
+        return e ? atoi(e) : 0;
+    }();
+    return v;
+}
+
 static int select(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype, const void* x, const void* w,
                   const void* y) {
+    if (ts_min_m() > 0 && M >= ts_min_m() && gemm_ts_supported(M, N, K, bits, gs, dtype, x, w, y)) return GBXQ_KERNEL_GEMM_TS;
     const bool skinny_ok = skinny_supported(M, N, K, bits, gs, dtype, x, w, y);
     const bool gemv_ok = gemv_supported(M, N, K, bits, gs, dtype, x, w, y);
     const bool gemm_ok = gemm_supported(M, N, K, bits, gs, dtype, x, w, y);
@@ -105,7 +116,11 @@ int gbxq_get_option(int key) {
 size_t gbxq_workspace_bytes(int64_t M, int64_t N, int64_t K, int bits, int group_size, int dtype) {
     // only the split-K path of the tensor-core GEMM (17..256 rows of x on a layer with few output tiles) uses scratch
     if (validate(M, N, K, bits, group_size, dtype) != GBXQ_OK || dtype != GBXQ_BF16) return 0;
-    if (select(M, N, K, bits, group_size, dtype, (const void*)16, (const void*)16, (const void*)16) != GBXQ_KERNEL_GEMM) return 0;
+    // sized for either tensor-core kernel whichever AUTO would pick (an explicit GBXQ_KERNEL_GEMM* request uses it too)
+    if (M <= 4) return 0;
+    const void* al = (const void*)16;
+    if (!gemm_supported(M, N, K, bits, group_size, dtype, al, al, al) && !gemm_ts_supported(M, N, K, bits, group_size, dtype, al, al, al))
+        return 0;
     return gemm_workspace_bytes(M, N, K);
 }
 
@@ -148,6 +163,9 @@ int gbxq_qmm_ex(const void* x, const uint32_t* qweight, const void* scales, cons
         case GBXQ_KERNEL_GEMM:
             if (!gemm_supported(M, N, K, bits, group_size, dtype, x, qweight, y)) return GBXQ_EUNSUPPORTED;
             return launch_gemm(x, qweight, scales, biases, bias, y, M, N, K, bits, group_size, workspace, workspace_bytes, st);
+        case GBXQ_KERNEL_GEMM_TS:
+            if (!gemm_ts_supported(M, N, K, bits, group_size, dtype, x, qweight, y)) return GBXQ_EUNSUPPORTED;
+            return launch_gemm_ts(x, qweight, scales, biases, bias, y, M, N, K, bits, group_size, workspace, workspace_bytes, st);
     }
     return GBXQ_EUNSUPPORTED;
 }

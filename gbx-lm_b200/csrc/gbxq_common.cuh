@@ -211,6 +211,10 @@ bool gemm_supported(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype
 int launch_gemm(const void* x, const uint32_t* w, const void* s, const void* b, const void* bias, void* y, int64_t M,
                 int64_t N, int64_t K, int bits, int gs, void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t gemm_workspace_bytes(int64_t M, int64_t N, int64_t K);
+bool gemm_ts_supported(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype, const void* x, const void* w,
+                       const void* y);
+int launch_gemm_ts(const void* x, const uint32_t* w, const void* s, const void* b, const void* bias, void* y, int64_t M,
+                   int64_t N, int64_t K, int bits, int gs, void* workspace, size_t workspace_bytes, cudaStream_t st);
 int launch_allreduce_oneshot(const void* in, void* out, int64_t count, int dtype, void* const* peer_bufs,
                              uint32_t* const* peer_flags, int64_t capacity, int rank, int world, uint32_t seq,
                              cudaStream_t st);
@@ -222,5 +226,8 @@ int device_sm_count();
 bool tma_encode_available();
 bool encode_tensor_map_2d(void* tm, int dtype, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
                           uint32_t box_inner, uint32_t box_outer, bool swizzle128);
+// the same with the swizzle span in bytes (0 = none, 32, 64, 128)
+bool encode_tensor_map_2d_sw(void* tm, int dtype, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                             uint32_t box_inner, uint32_t box_outer, int swizzle_bytes);
 
 }  // namespace gbxq

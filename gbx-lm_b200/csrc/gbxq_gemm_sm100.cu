@@ -535,6 +535,15 @@ bool encode_tensor_map_2d(void* tm, int dtype, const void* base, uint64_t inner,
                      swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
+bool encode_tensor_map_2d_sw(void* tm, int dtype, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                             uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                         : (swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE));
+    return encode_2d(reinterpret_cast<CUtensorMap*>(tm), dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT32,
+                     base, inner, outer, pitch_bytes, box_inner, box_outer, sw);
+}
+
 bool gemm_supported(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype, const void* x, const void* w,
                     const void* y) {
     if (dtype != GBXQ_BF16 || M < 1 || N < 1) return false;

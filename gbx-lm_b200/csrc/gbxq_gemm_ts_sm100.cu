@@ -1,0 +1,456 @@
+// gbxq_gemm_ts_sm100.cu -- quantized GEMM with the dequantised weights fed to the tensor core FROM TENSOR MEMORY
+// ("TS" form of tcgen05.mma: A in TMEM, B in shared memory).  Serves batches of 5..256 rows of x per tile (decode
+// batches 8..64 of BASELINE configs 2-5 and prefill chunks, gbx_lm/utils.py:312-319) behind
+// QuantizedLinear.__call__ -> mx.quantized_matmul(transpose=True) (gbx_lm/models/quantized_linear_gba.py:195-203).
+//
+// Why a second tensor-core kernel (gbxq_gemm_sm100.cu is the first): that kernel writes the dequantised bf16 tile to
+// shared memory in the UMMA layout, k-block by k-block, with a proxy fence and a barrier round trip per 64 k: measured
+// ~950 clocks per k-block (profiles/r01a_gemmbench.txt: 31-110 us per launch whatever the batch), 5x the HBM rate of
+// 4-bit weights, and every dequantised byte crosses shared memory twice (STS + the tensor core's operand read).  Here
+//   * a dequant thread owns ONE weight row (= one TMEM lane) and 32 consecutive k of a 128-k stage: one conflict-free
+//     128-bit shared-memory load of packed codes (the packed tile is fetched by TMA with the swizzle that makes a
+//     column of 16-byte pieces hit distinct banks), ~80 ALU instructions, ONE tcgen05.st of 16 columns -- no proxy
+//     fence, no shared-memory store, half as many barrier round trips per k;
+//   * swap-AB as before: weights are the MMA "A" operand (M = 128 output features = the 128 TMEM lanes, 8 columns per
+//     K = 16 step), tokens are the MMA N dimension (BN = 16..256 accumulator columns), x tiles arrive by TMA in the
+//     K-major 128B-swizzled layout;
+//   * TMEM: accumulator at columns [0, BN), four A stages of 64 columns at [256, 512);
+//   * x and packed weights have a producer warp each (x waits for the previous kernel of the stream -- programmatic
+//     dependent launch --, weights and scales are immutable and stream ahead of it);
+//   * split-K over blockIdx.z for skinny batches exactly as in gbxq_gemm_sm100.cu (deterministic reduction order).
+#include "gbxq_umma.cuh"
+
+namespace gbxq {
+
+void gemm_split_plan(int64_t M, int64_t N, int64_t K, int* splits, int* kb_per_split, size_t* ws_bytes);
+bool encode_tensor_map_2d_sw(void* tm, int dtype, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                             uint32_t box_inner, uint32_t box_outer, int swizzle_bytes);
+
+namespace {
+
+using namespace umma;
+
+constexpr int kStageK = 128;   // k per stage = 64 TMEM columns of A = 2 x tiles ("atoms") of 64 k
+constexpr int kAtomK = 64;
+constexpr int kTileN = 128;    // output features per CTA (= UMMA M = TMEM lanes)
+constexpr int kDqWarps = 16;   // warps 1..16: (row quarter = warp % 4, k quarter = (warp - 1) / 4)
+constexpr int kWarpMma = 17, kWarpW = 18;
+constexpr int kThreads = 19 * 32;
+constexpr int kAStages = 4;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kTmemAOff = 256;
+constexpr size_t kCntBytes = 16384;  // counter header of the split-K workspace (as gbxq_gemm_sm100.cu)
+
+struct TsParams {
+    const __nv_bfloat16* bias;
+    __nv_bfloat16* y;
+    int64_t M, N, K;
+    int gs_shift;
+    int splits, kb_per_split;  // split-K: blockIdx.z owns k-blocks [z * kb_per_split, ...) (multiples of 16 k-blocks)
+    float* ws;
+    uint32_t* cnt;
+    int early_w;               // 1: weights / scales are immutable while the call is in flight: fetch before griddepcontrol.wait
+};
+
+template <int BITS, int BN> struct Cfg {
+    static constexpr int XS = BN == 256 ? 5 : 8;                    // x atoms in flight (2 per stage)
+    static constexpr uint32_t B_BYTES = BN * kAtomK * 2;
+    static constexpr uint32_t W_ROW = 16 * BITS;                    // packed bytes of 128 codes
+    static constexpr uint32_t W_SLOT = kTileN * W_ROW;              // 2*BITS KB
+    static constexpr int WS_RAW = (48 * 1024) / W_SLOT;
+    static constexpr int WS = WS_RAW > 8 ? 8 : (WS_RAW < 3 ? 3 : WS_RAW);
+    static constexpr uint32_t S_SLOT = 2 * kTileN * 16;             // scales + biases of 8 groups per row
+    static constexpr int SS = 4;
+    static constexpr int NBAR = 2 * XS + 2 * WS + 2 * SS + 2 * kAStages + 1;
+    static constexpr size_t SMEM = (size_t)XS * B_BYTES + (size_t)WS * W_SLOT + (size_t)SS * S_SLOT + NBAR * 8 + 16 + 1024;
+};
+
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+
+// The 32 codes (k quarter kq of the stage) of tile row r from a packed-weight slot.  The slot was written by TMA with
+// Cfg::SWZ: 16-byte piece c of row r sits at piece c ^ f(r) so that the 8 lanes of an LDS wavefront (8 consecutive
+// rows, same quarter) read distinct bank groups.
+template <int BITS> __device__ __forceinline__ void load_codes(uint32_t slot, int r, int kq, uint32_t (&w)[BITS]) {
+    if constexpr (BITS == 4) {
+        const uint4 t = lds128(slot + (uint32_t)r * 64u + (uint32_t)((kq ^ ((r >> 1) & 3)) << 4));
+        w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+    } else if constexpr (BITS == 2) {
+        const uint2 t = lds64(slot + (uint32_t)r * 32u + (uint32_t)(((kq >> 1) ^ ((r >> 2) & 1)) << 4) + (uint32_t)(kq & 1) * 8u);
+        w[0] = t.x; w[1] = t.y;
+    } else if constexpr (BITS == 8) {
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const uint4 t = lds128(slot + (uint32_t)r * 128u + (uint32_t)(((2 * kq + i) ^ (r & 7)) << 4));
+            w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
+        }
+    } else if constexpr (BITS == 3) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) w[i] = lds32(slot + (uint32_t)r * 48u + (uint32_t)kq * 12u + 4u * i);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const uint2 t = lds64(slot + (uint32_t)r * 96u + (uint32_t)kq * 24u + 8u * i);
+            w[2 * i] = t.x; w[2 * i + 1] = t.y;
+        }
+    }
+}
+
+// 16-bit entry `g` (0..7) of a 16-byte row held in a uint4 (warp-uniform g)
+__device__ __forceinline__ uint32_t pick16(const uint4& v, int g) {
+    const int rs = g >> 1;
+    const uint32_t wv = rs == 0 ? v.x : (rs == 1 ? v.y : (rs == 2 ? v.z : v.w));
+    return (g & 1) ? (wv >> 16) : (wv & 0xffffu);
+}
+
+template <int BITS, int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_ts_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+               const __grid_constant__ CUtensorMap tmap_s, const __grid_constant__ CUtensorMap tmap_b, const TsParams p) {
+    using C = Cfg<BITS, BN>;
+    constexpr int XS = C::XS, WS = C::WS, SS = C::SS, AS = kAStages;
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* xring = smem;                                   // [XS][BN x 64] bf16, 128B-swizzled (TMA)
+    uint8_t* wring = xring + (size_t)XS * C::B_BYTES;        // [WS][128 rows x 128 codes] packed (TMA, swizzled)
+    uint8_t* sring = wring + (size_t)WS * C::W_SLOT;         // [SS][scales 128 x 8 | biases 128 x 8] bf16
+    uint64_t* full_b = reinterpret_cast<uint64_t*>(sring + (size_t)SS * C::S_SLOT);
+    uint64_t* empty_b = full_b + XS;
+    uint64_t* wfull = empty_b + XS;
+    uint64_t* wempty = wfull + WS;
+    uint64_t* sfull = wempty + WS;
+    uint64_t* sempty = sfull + SS;
+    uint64_t* full_a = sempty + SS;
+    uint64_t* empty_a = full_a + AS;
+    uint64_t* tmem_full = empty_a + AS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * kTileN;
+    const int m0 = blockIdx.y * BN;
+    const int st_all = (int)(p.K / kStageK);
+    const int st_lo = p.splits > 1 ? (int)blockIdx.z * (p.kb_per_split >> 1) : 0;    // first stage of this split
+    const int nst = p.splits > 1 ? min(p.kb_per_split >> 1, st_all - st_lo) : st_all;  // stages of this CTA
+    const int st_per_s = p.gs_shift == 5 ? 2 : (p.gs_shift == 6 ? 4 : 8);              // stages per scale slot (8 groups)
+    const int sl_lo = st_lo / st_per_s;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < XS; s++) {
+            mbar_init(&full_b[s], 1);    // x producer (+ tx bytes)
+            mbar_init(&empty_b[s], 1);   // tcgen05.commit
+        }
+#pragma unroll
+        for (int s = 0; s < WS; s++) {
+            mbar_init(&wfull[s], 1);
+            mbar_init(&wempty[s], kDqWarps);
+        }
+#pragma unroll
+        for (int s = 0; s < SS; s++) {
+            mbar_init(&sfull[s], 1);
+            mbar_init(&sempty[s], kDqWarps);
+        }
+#pragma unroll
+        for (int s = 0; s < AS; s++) {
+            mbar_init(&full_a[s], kDqWarps);
+            mbar_init(&empty_a[s], 1);   // tcgen05.commit
+        }
+        mbar_init(tmem_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmap_x);
+            tma_prefetch_desc(&tmap_w);
+            tma_prefetch_desc(&tmap_s);
+            tma_prefetch_desc(&tmap_b);
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, kTmemCols);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) griddep_launch();  // the next kernel of the stream may start its prologue when SMs free up
+
+    if (warp == 0) {
+        // ===================== x producer =====================
+        if (lane == 0) {
+            griddep_wait();  // x belongs to the previous kernels of the stream
+            for (int a = 0; a < 2 * nst; a++) {
+                const int s = a % XS;
+                mbar_wait(&empty_b[s], ((uint32_t)(a / XS) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(&full_b[s], C::B_BYTES);
+                tma_load_2d(xring + (size_t)s * C::B_BYTES, &tmap_x, (2 * st_lo + a) * kAtomK, m0, &full_b[s]);
+            }
+        }
+    } else if (warp == kWarpW) {
+        // ===================== packed-weight / scale producer =====================
+        if (lane == 0) {
+            if (!p.early_w) griddep_wait();
+            for (int s = 0; s < nst; s++) {
+                if (s % st_per_s == 0) {
+                    const int sl = s / st_per_s, ss = sl % SS;
+                    mbar_wait(&sempty[ss], ((uint32_t)(sl / SS) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(&sfull[ss], C::S_SLOT);
+                    tma_load_2d(sring + (size_t)ss * C::S_SLOT, &tmap_s, (sl_lo + sl) * 8, n0, &sfull[ss]);
+                    tma_load_2d(sring + (size_t)ss * C::S_SLOT + kTileN * 16, &tmap_b, (sl_lo + sl) * 8, n0, &sfull[ss]);
+                }
+                const int ws = s % WS;
+                mbar_wait(&wempty[ws], ((uint32_t)(s / WS) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(&wfull[ws], C::W_SLOT);
+                tma_load_2d(wring + (size_t)ws * C::W_SLOT, &tmap_w, (st_lo + s) * 4 * BITS, n0, &wfull[ws]);
+            }
+        }
+    } else if (warp == kWarpMma) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(kTileN, BN);
+            for (int s = 0; s < nst; s++) {
+                const int sa = s % AS;
+                mbar_wait(&full_a[sa], (uint32_t)(s / AS) & 1u);
+#pragma unroll
+                for (int a = 0; a < 2; a++) {
+                    const int ai = 2 * s + a, ax = ai % XS;
+                    mbar_wait(&full_b[ax], (uint32_t)(ai / XS) & 1u);
+                    tc_fence_after();
+                    const uint32_t b_addr = smem_u32(xring + (size_t)ax * C::B_BYTES);
+                    const uint32_t a_tmem = tmem_base + kTmemAOff + (uint32_t)(sa * 64 + a * 32);
+#pragma unroll
+                    for (int k = 0; k < kAtomK / 16; k++)
+                        mma_ts_f16(tmem_base, a_tmem + (uint32_t)(k * 8), make_sw128_kmajor_desc(b_addr + k * 32), idesc,
+                                   (s | a | k) != 0 ? 1u : 0u);
+                    mma_commit(&empty_b[ax]);   // the x tile is free once these MMAs retire
+                }
+                mma_commit(&empty_a[sa]);       // ... and so is the A stage
+            }
+            mma_commit(tmem_full);              // accumulator complete -> epilogue
+        }
+    } else {
+        // ===================== dequant warps (1..16), then epilogue =====================
+        const int dw = warp - 1;
+        const int rq = warp & 3;                 // TMEM lane quarter this warp may touch (hardware: warp id % 4)
+        const int kq = dw >> 2;                  // k quarter of the stage
+        const int r = rq * 32 + lane;            // tile row = TMEM lane
+        const uint32_t wring_u32 = smem_u32(wring), sring_u32 = smem_u32(sring);
+        const uint32_t a_lane = tmem_base + kTmemAOff + ((uint32_t)(rq * 32) << 16) + (uint32_t)(kq * 16);
+        uint4 sreg = make_uint4(0u, 0u, 0u, 0u), breg = sreg;
+
+        for (int s = 0; s < nst; s++) {
+            const int ws = s % WS;
+            mbar_wait(&wfull[ws], (uint32_t)(s / WS) & 1u);
+            uint32_t w[BITS];
+            load_codes<BITS>(wring_u32 + (uint32_t)ws * C::W_SLOT, r, kq, w);
+            const bool new_slot = (s % st_per_s) == 0;
+            int ss = 0;
+            if (new_slot) {
+                const int sl = s / st_per_s;
+                ss = sl % SS;
+                mbar_wait(&sfull[ss], (uint32_t)(sl / SS) & 1u);
+                sreg = lds128(sring_u32 + (uint32_t)ss * C::S_SLOT + (uint32_t)r * 16u);
+                breg = lds128(sring_u32 + (uint32_t)ss * C::S_SLOT + kTileN * 16u + (uint32_t)r * 16u);
+            }
+            const int gl = ((((st_lo + s) * kStageK) + kq * 32) >> p.gs_shift) & 7;  // group inside the 8-group slot
+            const uint32_t sraw = pick16(sreg, gl), braw = pick16(breg, gl);
+            uint32_t v[16];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                uint32_t o[4];
+                dequant8<BITS, BITS>(w, c, sraw, braw, o);
+                v[4 * c] = o[0]; v[4 * c + 1] = o[1]; v[4 * c + 2] = o[2]; v[4 * c + 3] = o[3];
+            }
+            const int sa = s % AS;
+            mbar_wait(&empty_a[sa], ((uint32_t)(s / AS) & 1u) ^ 1u);  // the MMAs that read this stage have retired
+            tc_fence_after();
+            tmem_st16(a_lane + (uint32_t)(sa * 64), v);
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&full_a[sa]);
+                mbar_arrive(&wempty[ws]);           // the packed words were consumed above
+                if (new_slot) mbar_arrive(&sempty[ss]);
+            }
+        }
+
+        // ---- epilogue: TMEM -> registers -> bf16 -> y[m, n]; warp drains its lane quarter and column quarter
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        griddep_wait();  // y may still be read by an earlier kernel of the stream
+        const int er = rq * 32 + lane;
+        const int64_t n = (int64_t)n0 + er;
+        const bool row_ok = n < p.N;
+        const float bias_f = (p.bias != nullptr && row_ok) ? __bfloat162float(p.bias[n]) : 0.f;
+        constexpr int QCOLS = BN / 4;
+        constexpr int STEP = QCOLS >= 32 ? 32 : (QCOLS >= 16 ? 16 : (QCOLS >= 8 ? 8 : 4));
+        const int cq = dw >> 2;
+#pragma unroll 1
+        for (int c0 = cq * QCOLS; c0 < (cq + 1) * QCOLS; c0 += STEP) {
+            uint32_t v[32];
+            tmem_ld<STEP>(tmem_base + ((uint32_t)(rq * 32) << 16) + (uint32_t)c0, v);
+            if (row_ok) {
+#pragma unroll
+                for (int j = 0; j < STEP; j++) {
+                    const int64_t m = (int64_t)m0 + c0 + j;
+                    if (m < p.M) {
+                        if (p.splits > 1) {
+                            p.ws[((size_t)blockIdx.z * p.M + m) * p.N + n] = __uint_as_float(v[j]);
+                        } else {
+                            float f = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[j])));
+                            if (p.bias != nullptr) f = __fadd_rn(f, bias_f);
+                            p.y[(size_t)m * p.N + n] = __float2bfloat16_rn(f);
+                        }
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        if (p.splits > 1) {
+            // the last split to arrive at this tile's counter adds the partial tiles in split order and writes y
+            __threadfence();
+            asm volatile("bar.sync 2, %0;" ::"n"(kDqWarps * 32) : "memory");
+            uint32_t* flag = tmem_slot + 1;
+            const uint32_t tile = blockIdx.y * gridDim.x + blockIdx.x;
+            if (warp == 1 && lane == 0) *flag = atomicAdd(p.cnt + tile, 1u) == (uint32_t)p.splits - 1u ? 1u : 0u;
+            asm volatile("bar.sync 2, %0;" ::"n"(kDqWarps * 32) : "memory");
+            if (*flag != 0u) {
+                __threadfence();
+                if (row_ok) {
+                    for (int c = cq * QCOLS; c < (cq + 1) * QCOLS; c++) {
+                        const int64_t m = (int64_t)m0 + c;
+                        if (m < p.M) {
+                            float acc = 0.f;
+                            for (int z = 0; z < p.splits; z++) acc += __ldcg(p.ws + ((size_t)z * p.M + m) * p.N + n);
+                            float f = __bfloat162float(__float2bfloat16_rn(acc));
+                            if (p.bias != nullptr) f = __fadd_rn(f, bias_f);
+                            p.y[(size_t)m * p.N + n] = __float2bfloat16_rn(f);
+                        }
+                    }
+                }
+                if (warp == 1 && lane == 0) p.cnt[tile] = 0u;  // left zero for the next launch
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+struct Maps {
+    CUtensorMap x, w, s, b;
+};
+
+template <int BITS, int BN>
+int launch_inst(const Maps& mp, const TsParams& p, cudaStream_t st) {
+    constexpr size_t smem = Cfg<BITS, BN>::SMEM;
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    auto kern = gemm_ts_kernel<BITS, BN>;
+    static DeviceOnce configured;
+    if (configured.need()) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return check_cuda(e);
+        configured.done();
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)((p.N + kTileN - 1) / kTileN), (unsigned)((p.M + BN - 1) / BN), (unsigned)(p.splits > 1 ? p.splits : 1));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = mmv_get_pdl_mode() > 0 ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mp.x, mp.w, mp.s, mp.b, p);
+    count_launch();
+    return check_cuda(e);
+}
+
+template <int BITS>
+int launch_bn(int bn, const Maps& mp, const TsParams& p, cudaStream_t st) {
+    switch (bn) {
+        case 16: return launch_inst<BITS, 16>(mp, p, st);
+        case 32: return launch_inst<BITS, 32>(mp, p, st);
+        case 64: return launch_inst<BITS, 64>(mp, p, st);
+        case 128: return launch_inst<BITS, 128>(mp, p, st);
+        default: return launch_inst<BITS, 256>(mp, p, st);
+    }
+}
+
+int pick_bn(int64_t M) { return M <= 16 ? 16 : (M <= 32 ? 32 : (M <= 64 ? 64 : (M <= 128 ? 128 : 256))); }
+
+}  // namespace
+
+bool gemm_ts_supported(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype, const void* x, const void* w,
+                       const void* y) {
+    if (dtype != GBXQ_BF16 || M < 1 || N < 1) return false;
+    if (K % kStageK) return false;
+    if ((K * bits / 8) % 16) return false;      // TMA: packed row pitch must be a multiple of 16 bytes
+    if (((K / gs) * 2) % 16) return false;      // TMA: scale row pitch must be a multiple of 16 bytes
+    if (((uintptr_t)x | (uintptr_t)w) & 15) return false;
+    if ((uintptr_t)y & 1) return false;
+    if (M > (int64_t)1 << 24 || (N + kTileN - 1) / kTileN > 65535 * 32) return false;
+    return tma_encode_available();
+}
+
+int launch_gemm_ts(const void* x, const uint32_t* w, const void* s, const void* b, const void* bias, void* y, int64_t M,
+                   int64_t N, int64_t K, int bits, int gs, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    if (!tma_encode_available()) return GBXQ_EUNSUPPORTED;
+    if (((uintptr_t)s | (uintptr_t)b) & 15) return GBXQ_EUNSUPPORTED;
+    const int bn = pick_bn(M);
+    if ((M + bn - 1) / bn > 65535) return GBXQ_EUNSUPPORTED;
+    Maps mp;
+    const uint64_t words = (uint64_t)(K * bits / 32), G = (uint64_t)(K / gs);
+    const int swz = bits == 4 ? 64 : (bits == 2 ? 32 : (bits == 8 ? 128 : 0));
+    bool ok = encode_tensor_map_2d_sw(&mp.x, 0, x, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, kAtomK, (uint32_t)bn, 128);
+    ok = ok && encode_tensor_map_2d_sw(&mp.w, 1, w, words, (uint64_t)N, words * 4, (uint32_t)(4 * bits), kTileN, swz);
+    ok = ok && encode_tensor_map_2d_sw(&mp.s, 0, s, G, (uint64_t)N, G * 2, 8, kTileN, 0);
+    ok = ok && encode_tensor_map_2d_sw(&mp.b, 0, b, G, (uint64_t)N, G * 2, 8, kTileN, 0);
+    if (!ok) return GBXQ_EUNSUPPORTED;
+    TsParams p{};
+    p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+    p.y = reinterpret_cast<__nv_bfloat16*>(y);
+    p.M = M;
+    p.N = N;
+    p.K = K;
+    p.gs_shift = gs == 32 ? 5 : (gs == 64 ? 6 : 7);
+    p.splits = 1;
+    p.early_w = mmv_get_pdl_mode() >= 2 ? 1 : 0;
+    {
+        int sp, per;
+        size_t need;
+        gemm_split_plan(M, N, K, &sp, &per, &need);
+        if (sp > 1 && workspace != nullptr && workspace_bytes >= need && !((uintptr_t)workspace & 15)) {
+            p.splits = sp;
+            p.kb_per_split = per;
+            p.cnt = reinterpret_cast<uint32_t*>(workspace);
+            p.ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + kCntBytes);
+        }
+    }
+    switch (bits) {
+        case 2: return launch_bn<2>(bn, mp, p, st);
+        case 3: return launch_bn<3>(bn, mp, p, st);
+        case 4: return launch_bn<4>(bn, mp, p, st);
+        case 6: return launch_bn<6>(bn, mp, p, st);
+        case 8: return launch_bn<8>(bn, mp, p, st);
+    }
+    return GBXQ_EINVAL_BITS;
+}
+
+}  // namespace gbxq

@@ -44,7 +44,7 @@ int launch_inst(const Mmv8Params& p, const ArParams& ar, const Plan& pl, cudaStr
     auto kern = mmv8_kernel<BITS, GS, MT, CPW, R>;
     static DeviceOnce configured;  // per device: the attribute is a per-device property
     if (configured.need()) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCap);
         if (e != cudaSuccess) return check_cuda(e);
         configured.done();
     }
@@ -65,7 +65,10 @@ int launch_inst(const Mmv8Params& p, const ArParams& ar, const Plan& pl, cudaStr
 
 template <int BITS, int GS, int MT>
 int launch_cpw(const Mmv8Params& p, const ArParams& ar, const Plan& pl, cudaStream_t st) {
-    if (pl.R == 8) {
+    if (pl.R == 16) {
+        if constexpr (MT <= 2)
+            if (pl.cpw == 1) return launch_inst<BITS, GS, MT, 1, 16>(p, ar, pl, st);
+    } else if (pl.R == 8) {
         if (pl.cpw == 1) return launch_inst<BITS, GS, MT, 1, 8>(p, ar, pl, st);
         if (pl.cpw == 2) return launch_inst<BITS, GS, MT, 2, 8>(p, ar, pl, st);
     } else if (pl.R == 4) {

@@ -7,13 +7,21 @@
 namespace gbxq {
 namespace mmv8 {
 
-constexpr int kCW = 8;                        // consumer warps
+#ifndef GBXQ_MMV8_CW
+#define GBXQ_MMV8_CW 16
+#endif
+// consumer warps: 16 = one CTA per SM (default since r02p/r02q: the x -> digit conversion is done once per SM instead of
+// once per co-resident CTA: down_proj K = 14336 10.1 -> 9.0 us, 70B step 0.69 -> 0.72, bpw-2.2 0.31 -> 0.35), 8 = two
+// CTAs per SM (-DGBXQ_MMV8_CW=8: the round-1 geometry, 0.8 us faster on a lone 14336 x 4096 launch)
+constexpr int kCW = GBXQ_MMV8_CW;
+constexpr int kWide = kCW / 8;                // shared memory, stage and ring budgets scale with the CTA
+constexpr int kSmemCap = 110 * 1024 * kWide;
 constexpr int kThreads = (kCW + 1) * 32;      // + producer warp
 constexpr int kMaxStages = 8;                // barrier slots; one-call launches plan at most kPlanStages
 constexpr int kPlanStages = 4;
 constexpr int kArMaxCtas = GBXQ_RP_MAX_CTAS;
 #ifndef GBXQ_MMV8_MINCTAS
-#define GBXQ_MMV8_MINCTAS 2
+#define GBXQ_MMV8_MINCTAS (GBXQ_MMV8_CW == 8 ? 2 : 1)
 #endif
 constexpr int kMinCtas = GBXQ_MMV8_MINCTAS;    // register cap 112; a cap of 72 (3 CTAs / SM) measured 15 % slower
 constexpr int S = 4;                          // group slices per chunk column (= 8 columns / 2 digits)
@@ -671,7 +679,7 @@ inline int env_int(const char* name, int dflt) {
 }
 
 // grid_want > 0: the number of CTAs this layer may use (a segment of a grouped launch); 0: the whole device
-inline Plan make_plan(int64_t M, int64_t N, int64_t K, int bits, int gs, int grid_want = 0) {
+inline Plan make_plan(int64_t M, int64_t N, int64_t K, int bits, int gs, int grid_want = 0, bool allow_r16 = true) {
     Plan pl{};
     if (!(bits == 2 || bits == 3 || bits == 4 || bits == 6 || bits == 8) || M < 1 || M > 4 || N < 1) return pl;
     if ((bits == 2 || bits == 3 || bits == 6) && gs == 32) return pl;  // a thread chunk would be a fraction of a word
@@ -686,12 +694,14 @@ inline Plan make_plan(int64_t M, int64_t N, int64_t K, int bits, int gs, int gri
     pl.mt = M == 1 ? 1 : (M == 2 ? 2 : 4);
     pl.nch = (int)(G / S);
     static const int force_cpw = env_int("GBXQ_MMV8_CPW", 0);
-    static const int grid_mult = env_int("GBXQ_MMV8_GRID_MULT", 2);
-    static const int stage_kb = env_int("GBXQ_MMV8_STAGE_KB", 32);
-    static const int ring_kb = env_int("GBXQ_MMV8_RING_KB", 96);
+    static const int grid_mult = env_int("GBXQ_MMV8_GRID_MULT", 2 / kWide);
+    static const int stage_kb = env_int("GBXQ_MMV8_STAGE_KB", 32 * kWide);
+    static const int ring_kb = env_int("GBXQ_MMV8_RING_KB", 96 * kWide);
+    static const int two_cols_from = env_int("GBXQ_MMV8_TWOCOLS", kCW == 8 ? 8 : 32);
+    static const int r16 = env_int("GBXQ_MMV8_R16", kCW == 16 ? 1 : 0);
     // chunk columns per warp: the smallest power of two that covers the row with 8 warps, but at least 2 (two
     // independent MMA chains per set) when the row has 8 columns or more
-    pl.cpw = pl.nch >= 8 ? 2 : 1;
+    pl.cpw = pl.nch >= two_cols_from ? 2 : 1;
     while ((pl.nch + pl.cpw - 1) / pl.cpw > kCW && pl.cpw < 8) pl.cpw *= 2;
     if (force_cpw) pl.cpw = force_cpw;
     if (!(pl.cpw == 1 || pl.cpw == 2 || pl.cpw == 4 || pl.cpw == 8)) return pl;
@@ -699,7 +709,9 @@ inline Plan make_plan(int64_t M, int64_t N, int64_t K, int bits, int gs, int gri
     if (pl.cw > kCW) return pl;
     pl.rg = kCW / pl.cw;
     pl.R = pl.cpw <= 2 ? 8 : 4;
-    if ((int64_t)pl.R * row_bytes > (int64_t)stage_kb * 1024) pl.R = 4;
+    // one chunk column per warp and 16 warps: 16 rows per warp and stage keep a stage at 2 x 16 rows of a 2/4 KB row
+    if (r16 && allow_r16 && pl.cpw == 1 && pl.nch > kCW / 2 && M <= 2 && 16 * row_bytes <= (int64_t)stage_kb * 1024) pl.R = 16;
+    if (pl.R == 8 && (int64_t)pl.R * row_bytes > (int64_t)stage_kb * 1024) pl.R = 4;
     if ((int64_t)pl.R * row_bytes > (int64_t)stage_kb * 1024) return pl;
     while (pl.rg > 1 && (int64_t)pl.rg * pl.R * row_bytes > (int64_t)stage_kb * 1024 / 2) pl.rg--;
     pl.tr = pl.rg * pl.R;
@@ -717,7 +729,7 @@ inline Plan make_plan(int64_t M, int64_t N, int64_t K, int bits, int gs, int gri
     const int64_t rows_max = ((N / pl.row_unit + grid - 1) / grid) * pl.row_unit;
     pl.smem = (size_t)pl.stages * pl.slot_bytes + 2 * kMaxStages * 8 + (size_t)kCW * pl.cpw * S * pl.mt * 4 +
               (size_t)rows_max * 2 * pl.cw * pl.mt * 4 + 16;
-    if (pl.smem > 110 * 1024) return pl;
+    if (pl.smem > (size_t)kSmemCap) return pl;
     pl.ok = true;
     return pl;
 }
@@ -731,7 +743,7 @@ inline double segment_cost(int64_t N, int64_t K, int bits, int gs) {
 }
 
 inline int mmv8_total_ctas() {
-    static const int grid_mult = env_int("GBXQ_MMV8_GRID_MULT", 2);
+    static const int grid_mult = env_int("GBXQ_MMV8_GRID_MULT", 2 / kWide);
     return device_sm_count() * grid_mult;
 }
 

@@ -62,7 +62,7 @@ int launch_inst2(const GroupParams& gp, int grid, size_t smem, cudaStream_t st) 
     auto kern = mmv8_grouped_kernel<GS, MT, CPW, R, ODD>;
     static DeviceOnce configured;  // per device: the attribute is a per-device property
     if (configured.need()) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCap);
         if (e != cudaSuccess) return check_cuda(e);
         configured.done();
     }
@@ -90,7 +90,10 @@ int launch_inst(const GroupParams& gp, int grid, size_t smem, cudaStream_t st) {
 
 template <int GS, int MT>
 int launch_cpw(const GroupParams& gp, int cpw, int R, int grid, size_t smem, cudaStream_t st) {
-    if (R == 8) {
+    if (R == 16) {
+        if constexpr (MT <= 2)
+            if (cpw == 1) return launch_inst<GS, MT, 1, 16>(gp, grid, smem, st);
+    } else if (R == 8) {
         if (cpw == 1) return launch_inst<GS, MT, 1, 8>(gp, grid, smem, st);
         if (cpw == 2) return launch_inst<GS, MT, 2, 8>(gp, grid, smem, st);
     } else if (R == 4) {

@@ -36,7 +36,7 @@ using namespace mmv8;
 namespace {
 
 constexpr int kDescBytes = 4096;          // shared-memory descriptor rings (consumers 2, producer 4) in front of the weight ring
-constexpr size_t kStreamSmemMax = 112 * 1024;
+constexpr size_t kStreamSmemMax = 112 * 1024 * kWide;
 
 inline int variant_of(int cpw, int R) {  // (CPW, R): (1,8) (2,8) (1,4) (2,4) (4,4) (8,4)
     if (R == 8) return cpw == 1 ? 0 : (cpw == 2 ? 1 : -1);
@@ -288,7 +288,7 @@ int stream_plan(const gbxq_stream_call* calls, int ncalls, int64_t M, int dtype,
         for (int i = 0; given < total_ctas; i = (i + 1) % cl.nseg, given++) ctas[i]++;
         for (int i = 0; i < cl.nseg; i++) {
             const gbxq_segment& sg = cl.segs[i];
-            const Plan pl = make_plan(M, sg.N, cl.K, sg.bits, gs, ctas[i]);
+            const Plan pl = make_plan(M, sg.N, cl.K, sg.bits, gs, ctas[i], false);
             if (!pl.ok || pl.cpw * pl.mt > 8 || variant_of(pl.cpw, pl.R) < 0) return GBXQ_EUNSUPPORTED;
             const Plan& first = plans[(size_t)c * GBXQ_MAX_SEGMENTS].pl;
             if (i > 0 && (pl.cpw != first.cpw || pl.R != first.R)) return GBXQ_EUNSUPPORTED;

@@ -20,7 +20,7 @@ import torch
 from . import _lib
 
 _DT = {torch.bfloat16: _lib.BF16, torch.float16: _lib.F16, torch.float32: _lib.F32}
-_KERNELS = {"auto": 0, "generic": 1, "gemv": 2, "gemm": 3, "skinny": 4, "mmv": 5, "mmv8": 6}
+_KERNELS = {"auto": 0, "generic": 1, "gemv": 2, "gemm": 3, "skinny": 4, "mmv": 5, "mmv8": 6, "gemm_ts": 7}
 
 
 def _dt(t: torch.Tensor) -> int:
@@ -120,7 +120,7 @@ def _qmm_impl(x, w, scales, biases, bias, group_size: int, bits: int, kernel: in
     y = torch.empty((m, n), dtype=x.dtype, device=x.device)
     with torch.cuda.device(x.device):
         st = torch.cuda.current_stream().cuda_stream
-        ws, ws_bytes = _workspace(x.device, st, m, n, k, bits, group_size, dt) if m > 16 else (None, 0)
+        ws, ws_bytes = _workspace(x.device, st, m, n, k, bits, group_size, dt) if m > 4 else (None, 0)
         rc = _lib.get().gbxq_qmm_ex(
             x2.data_ptr(), w.data_ptr(), scales.data_ptr(), biases.data_ptr(),
             bias.data_ptr() if bias is not None else None, y.data_ptr(),

@@ -71,9 +71,11 @@ typedef enum gbxq_kernel {
     GBXQ_KERNEL_GEMM = 3,    /* tcgen05/TMEM tensor-core GEMM with in-kernel dequant (bf16) */
     GBXQ_KERNEL_SKINNY = 4,  /* mma.sync skinny matmul, 8 tokens per pass, 2/4/8-bit (bf16)  */
     GBXQ_KERNEL_MMV = 5,     /* bf16 tensor-pipe decode matrix-vector kernel, 1..4 tokens, 2/4/8-bit, PDL */
-    GBXQ_KERNEL_MMV8 = 6     /* integer tensor-pipe (IMMA u8 x s8) decode kernel: codes used in place, activations as
-                                per-group 15-bit block fixed point; 1..4 tokens, 2/4/8-bit (bf16 in/out), PDL.
+    GBXQ_KERNEL_MMV8 = 6,    /* integer tensor-pipe (IMMA u8 x s8) decode kernel: codes used in place, activations as
+                                per-group 15-bit block fixed point; 1..4 tokens, every width (bf16 in/out), PDL.
                                 GBXQ_KERNEL_AUTO picks it for M <= 2 and the skinny kernel from M = 3 */
+    GBXQ_KERNEL_GEMM_TS = 7  /* tcgen05 GEMM with the dequantised weights as the TMEM ("TS") operand: one weight row
+                                per thread, no shared-memory round trip of the bf16 tile; K % 128 == 0 (bf16), PDL */
 } gbxq_kernel;
 
 /* Process-wide options (gbxq_set_option / gbxq_get_option). */

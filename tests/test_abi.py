@@ -79,7 +79,7 @@ def test_stream_plan_is_host_only_and_validates():
              call(4096, [(4, 14336, 64), (4, 14336, 64)]), call(14336, [(4, 4096, 64)])]
     rc, info, arr = plan(block * 4)
     assert rc == 0 and info.ncalls == 16 and info.grid % 2 == 0 and info.group_size == 64 and info.mt == 1
-    assert 2 <= info.stages <= 8 and info.smem_bytes <= 112 * 1024 and info.stages * info.slot_bytes < info.smem_bytes
+    assert 2 <= info.stages <= 8 and info.smem_bytes <= 224 * 1024 and info.stages * info.slot_bytes < info.smem_bytes
     assert info.counter_bytes == (16 + 2) * 4 and info.blob_bytes > 0
     buf = ctypes.create_string_buffer(int(info.blob_bytes))
     assert lib.gbxq_stream_plan(arr, 16, 1, 0, buf, info.blob_bytes - 1, ctypes.byref(info)) == -8  # blob too small
@@ -192,7 +192,7 @@ def test_stream_plan_blob_invariants():
                 assert (N, K, bits[s], Mv) == (sg.N, c.K, sg.bits, M) and wq == sg.qweight and xq == c.x
                 assert G == K // sg.group_size and row_bytes == K * sg.bits // 8 and nch * 4 == G
                 assert grid_s >= 1 and rows_base * grid_s + rows_rem == N and 0 <= rows_rem < grid_s  # every row once
-                assert 1 <= cw * rg <= 8 and tr % 4 == 0 and spr0 % 4 == 0 and spr1 % 4 == 0 and 0 < spr0 <= tr and spr1 <= tr
+                assert 1 <= cw * rg <= 16 and tr % 4 == 0 and spr0 % 4 == 0 and spr1 % 4 == 0 and 0 < spr0 <= tr and spr1 <= tr
                 assert stages == info.stages and slot_bytes == info.slot_bytes and early == 1
                 assert tr * row_bytes <= sb_off and sb_off + 2 * tr * G * 2 <= slot_bytes
-        assert 4096 + info.stages * info.slot_bytes < info.smem_bytes <= 112 * 1024
+        assert 4096 + info.stages * info.slot_bytes < info.smem_bytes <= 224 * 1024

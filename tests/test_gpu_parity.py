@@ -289,6 +289,74 @@ def test_qmm_gemm_split_k(cuda_device, M, N, K, bits, gs):
     assert torch.equal(ys[0], g.quantized_matmul(x, d["qweight"], d["scales"], d["zeros"], True, gs, bits, bias=d["bias"]))
 
 
+@pytest.mark.parametrize("bits", BITS)
+@pytest.mark.parametrize("gs", GS)
+def test_qmm_gemm_ts_vs_oracle(cuda_device, bits, gs):
+    """tcgen05 GEMM with the dequantised weights as the TMEM operand (gbxq_gemm_ts_sm100.cu): every token tile width
+    (16 .. 256 accumulator columns, several token tiles), ragged N (rows past N are zero-filled by TMA), K a multiple of
+    the 128-k stage; tolerance = the path's 1e-2 (north_star)."""
+    g = _ops()
+    for (M, N, K) in ((5, 128, 1024), (16, 200, 1024), (17, 130, 2048), (33, 384, 1024), (100, 256, 2048), (200, 128, 1024),
+                      (300, 130, 4096)):
+        _run_case(g, cuda_device, "gemm_ts", bits, gs, M, N, K, seed=bits + gs + M, with_bias=(M == 100), tol=1e-2)
+
+
+@pytest.mark.parametrize("M,N,K,bits,gs", [(8, 512, 4096, 4, 64), (32, 512, 4096, 4, 64), (64, 640, 6144, 4, 128), (17, 128, 8192, 2, 64),
+                                          (256, 1024, 3072, 8, 64), (100, 384, 5120, 3, 64), (48, 256, 4096, 6, 32)])
+def test_qmm_gemm_ts_split_k(cuda_device, M, N, K, bits, gs):
+    """Split-K of the TMEM-operand GEMM: against the oracle, bitwise reproducible call after call (tile counters left
+    zero), bias as a separately rounded add, and equal to the shared-memory-operand GEMM within fp32 summation noise."""
+    g = _ops()
+    from gbx_lm_b200 import _lib
+
+    assert _lib.get().gbxq_workspace_bytes(M, N, K, bits, gs, 0) > 16384, "shape does not exercise split-K"
+    L = A.synth_layer(N, K, bits, gs, seed=M + N, with_bias=True)
+    d = layer_to_cuda(L, cuda_device)
+    xb = A.synth_x(M, K, seed=K)
+    x = bf16_from_bits(xb, cuda_device)
+    ys = [g.quantized_matmul(x, d["qweight"], d["scales"], d["zeros"], True, gs, bits, bias=d["bias"], kernel="gemm_ts") for _ in range(3)]
+    y0 = g.quantized_matmul(x, d["qweight"], d["scales"], d["zeros"], True, gs, bits, kernel="gemm_ts")
+    ref = A.quantized_matmul(xb, L["qweight"], L["scales"], L["zeros"], gs, bits, "bf16", "f64")
+    assert_close_to_truth(y0, ref, f"gemm_ts split-K M{M} N{N} K{K} b{bits}", 1e-2)
+    assert torch.equal(ys[0], (y0.float() + d["bias"].float()).to(torch.bfloat16))
+    assert torch.equal(ys[0], ys[1]) and torch.equal(ys[0], ys[2])
+    if M >= 17:
+        y1 = g.quantized_matmul(x, d["qweight"], d["scales"], d["zeros"], True, gs, bits, kernel="gemm")
+        assert (y0.float() - y1.float()).abs().max() <= 2.0 ** -6 * y1.float().abs().max()
+
+
+def test_qmm_gemm_ts_model_shapes_and_pdl(cuda_device):
+    """Model-sized calls at decode batches (8B q/o, gate, down at 8 / 32 / 64 rows of x), launched back to back with and
+    without programmatic dependent launch: y of one call is x of the next (the x producer waits for the previous kernel,
+    the weight producer does not)."""
+    g = _ops()
+    from gbx_lm_b200 import ops
+
+    try:
+        for pdl in (0, 2):
+            ops.set_pdl_mode(pdl)
+            for (M, N, K, bits) in ((8, 4096, 4096, 4), (32, 14336, 4096, 2), (64, 4096, 14336, 4)):
+                _run_case(g, cuda_device, "gemm_ts", bits, 64, M, N, K, seed=M + bits, tol=1e-2)
+            # chain: x -> A (K -> K) -> B (K -> K), three times on one stream without synchronising in between
+            K = 2048
+            LA, LB = A.synth_layer(K, K, 4, 64, seed=5), A.synth_layer(K, K, 4, 64, seed=6)
+            dA, dB = layer_to_cuda(LA, cuda_device), layer_to_cuda(LB, cuda_device)
+            xb = A.synth_x(24, K, seed=7)
+            x = bf16_from_bits(xb, cuda_device)
+            outs = []
+            for _ in range(3):
+                h = g.quantized_matmul(x, dA["qweight"], dA["scales"], dA["zeros"], True, 64, 4, kernel="gemm_ts")
+                outs.append(g.quantized_matmul(h, dB["qweight"], dB["scales"], dB["zeros"], True, 64, 4, kernel="gemm_ts"))
+            torch.cuda.synchronize()
+            h_ref = g.quantized_matmul(x, dA["qweight"], dA["scales"], dA["zeros"], True, 64, 4, kernel="generic")
+            ref = A.quantized_matmul(bits_from_bf16(h), LB["qweight"], LB["scales"], LB["zeros"], 64, 4, "bf16", "f64")
+            assert (h.float() - h_ref.float()).abs().max() <= 1e-2 * h_ref.float().abs().max()
+            assert_close_to_truth(outs[0], ref, "gemm_ts chain", 1e-2)
+            assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    finally:
+        ops.set_pdl_mode(2)
+
+
 def test_qmm_gemm_declines_unaligned_pitch(cuda_device):
     """K = 256 with gs = 128 gives a 4-byte scale row pitch: the forced tensor-core kernel refuses
     (no silent fallback), auto dispatch serves the call with another kernel."""

@@ -29,14 +29,20 @@ def bench(n, k, bits, gs, m, kernel, dev, iters=10):
     s = ((torch.rand((n, k // gs), generator=gen, device=dev) + 0.5) * (2.0 / (k ** 0.5) / nb)).to(torch.bfloat16)
     z = (-s.float() * (nb / 2.0)).to(torch.bfloat16)
     x = torch.randn((m, k), generator=gen, device=dev).to(torch.bfloat16)
-    kid = {"auto": 0, "generic": 1, "gemv": 2, "gemm": 3, "skinny": 4, "mmv": 5, "mmv8": 6}[kernel]
+    kid = {"auto": 0, "generic": 1, "gemv": 2, "gemm": 3, "skinny": 4, "mmv": 5, "mmv8": 6, "gemm_ts": 7}[kernel]
     for i in range(3):
         ops._qmm_impl(x, ws[i % copies], s, z, None, gs, bits, kid)
     torch.cuda.synchronize()
+    # one CUDA graph of `iters` launches: host-side launch cost (tensor-map encodes, Python) stays out of the timing
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for i in range(iters):
+            ops._qmm_impl(x, ws[i % copies], s, z, None, gs, bits, kid)
+    graph.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(iters):
-        ops._qmm_impl(x, ws[i % copies], s, z, None, gs, bits, kid)
+    graph.replay()
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / iters

@@ -32,7 +32,7 @@ def bench_shape(n, k, bits, gs, m, kernel, dev, iters=30, min_bytes=320 << 20, l
         ss.append(s)
         zs.append((-s.float() * (nb / 2.0)).to(torch.bfloat16))
     x = torch.randn((m, k), generator=gen, device=dev).to(torch.bfloat16)
-    kid = {"auto": 0, "generic": 1, "gemv": 2, "gemm": 3, "skinny": 4, "mmv": 5, "mmv8": 6}[kernel]
+    kid = {"auto": 0, "generic": 1, "gemv": 2, "gemm": 3, "skinny": 4, "mmv": 5, "mmv8": 6, "gemm_ts": 7}[kernel]
 
     def run(i):
         j = i % copies

@@ -21,7 +21,7 @@ ws = [torch.randint(-(2 ** 31), 2 ** 31 - 1, (n, k * bits // 32), generator=gen,
 s = ((torch.rand((n, k // gs), generator=gen, device=dev) + 0.5) * (2.0 / (k ** 0.5) / nb)).to(torch.bfloat16)
 z = (-s.float() * (nb / 2.0)).to(torch.bfloat16)
 x = torch.randn((m, k), generator=gen, device=dev).to(torch.bfloat16)
-kid = {"auto": 0, "generic": 1, "gemv": 2, "gemm": 3, "skinny": 4, "mmv": 5, "mmv8": 6}[kernel]
+kid = {"auto": 0, "generic": 1, "gemv": 2, "gemm": 3, "skinny": 4, "mmv": 5, "mmv8": 6, "gemm_ts": 7}[kernel]
 for i in range(iters):
     y = ops._qmm_impl(x, ws[i % copies], s, z, None, gs, bits, kid)
 torch.cuda.synchronize()
