@@ -38,6 +38,7 @@ EXPORTS = (
     "gbxq_add_rmsnorm",
     "gbxq_silu_mul",
     "gbxq_head_gemv",
+    "gbxq_gather_qmm",
 )
 
 
@@ -144,6 +145,8 @@ def get() -> ctypes.CDLL:
     lib.gbxq_silu_mul.argtypes = [vp, vp, vp, i64, vp]
     lib.gbxq_head_gemv.restype = ci
     lib.gbxq_head_gemv.argtypes = [vp, vp, vp, i64, i64, i64, ci, vp]
+    lib.gbxq_gather_qmm.restype = ci
+    lib.gbxq_gather_qmm.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, ci, ci, ci, ci, vp]
     lib.gbxq_allreduce_oneshot.restype = ci
     lib.gbxq_allreduce_oneshot.argtypes = [vp, vp, i64, ci, vp, vp, i64, ci, ci, u32, vp]
     lib.gbxq_qmm_rowpar_allreduce.restype = ci

@@ -28,6 +28,7 @@ SOURCES = [
     "gbxq_stream.cu",
     "gbxq_glue.cu",
     "gbxq_head.cu",
+    "gbxq_gather.cu",
     "gbxq_gemm_sm100.cu",
     "gbxq_gemm_ts_sm100.cu",
     "gbxq_allreduce.cu",

@@ -230,6 +230,26 @@ int gbxq_head_gemv(const void* x, const void* weight, void* y, int64_t M, int64_
     return launch_head_gemv(x, weight, y, M, V, K, (cudaStream_t)stream);
 }
 
+int gbxq_gather_qmm(const void* x, const uint32_t* qweight, const void* scales, const void* biases, const void* bias,
+                    const int32_t* lhs_indices, const int32_t* rhs_indices, void* y, int64_t R, int64_t XB, int64_t E,
+                    int64_t M, int64_t N, int64_t K, int transpose, int bits, int group_size, int dtype, void* stream) {
+    // the quantized axis is K for transpose = 1 (rows of an [N, K] matrix) and N for transpose = 0 (rows of a [K, N] one)
+    const int rc = transpose ? validate(M, N, K, bits, group_size, dtype) : validate(M, K, N, bits, group_size, dtype);
+    if (rc != GBXQ_OK) return rc;
+    if (R < 0 || XB < 0 || E < 0 || K <= 0 || N < 0) return GBXQ_ESHAPE;
+    if (R == 0 || M == 0 || N == 0) return GBXQ_OK;
+    if (XB == 0 || E == 0) return GBXQ_ESHAPE;
+    if (lhs_indices == nullptr && R > XB) return GBXQ_ESHAPE;
+    if (rhs_indices == nullptr && R > E) return GBXQ_ESHAPE;
+    if (!x || !qweight || !scales || !biases || !y) return GBXQ_ENULL;
+    if (!transpose && bias != nullptr) return GBXQ_EUNSUPPORTED;
+    const size_t esz = dtype == GBXQ_F32 ? 4 : 2;
+    if (((uintptr_t)x | (uintptr_t)y | (uintptr_t)scales | (uintptr_t)biases | (uintptr_t)bias) & (esz - 1)) return GBXQ_EALIGN;
+    if (((uintptr_t)qweight | (uintptr_t)lhs_indices | (uintptr_t)rhs_indices) & 3) return GBXQ_EALIGN;
+    return launch_gather_qmm(x, qweight, scales, biases, bias, lhs_indices, rhs_indices, y, R, XB, E, M, N, K, transpose ? 1 : 0,
+                             bits, group_size, dtype, (cudaStream_t)stream);
+}
+
 int gbxq_stream_plan(const gbxq_stream_call* calls_host, int ncalls, int64_t M, int dtype, void* host_blob,
                      size_t blob_capacity, gbxq_stream_info* info) {
     return stream_plan(calls_host, ncalls, M, dtype, host_blob, blob_capacity, info);

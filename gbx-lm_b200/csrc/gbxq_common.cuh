@@ -204,6 +204,9 @@ int launch_add_rmsnorm(const void* x, const void* r, const void* w, float eps, v
                        cudaStream_t st);
 int launch_silu_mul(const void* g, const void* u, void* out, int64_t n, cudaStream_t st);
 int launch_head_gemv(const void* x, const void* w, void* y, int64_t M, int64_t V, int64_t K, cudaStream_t st);
+int launch_gather_qmm(const void* x, const uint32_t* w, const void* s, const void* b, const void* bias, const int32_t* lhs,
+                      const int32_t* rhs, void* y, int64_t R, int64_t XB, int64_t E, int64_t M, int64_t N, int64_t K,
+                      int transpose, int bits, int gs, int dtype, cudaStream_t st);
 void mmv_set_pdl_mode(int mode);
 int mmv_get_pdl_mode();
 bool gemm_supported(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype, const void* x, const void* w,

@@ -29,6 +29,8 @@
 //               stage's smem release and, at the end, the accumulator hand-off to the epilogue
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "gbxq_common.cuh"
 
 namespace gbxq {
@@ -488,8 +490,15 @@ bool encode_2d(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, uint64
     const cuuint64_t gstride[1] = {pitch_bytes};
     const cuuint32_t box[2] = {box_inner, box_outer};
     const cuuint32_t estr[2] = {1, 1};
-    return enc(tm, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    static const int promo = [] {  // GBXQ_TMA_L2PROMO = 0 / 64 / 128 / 256 (development switch; default 256 bytes)
+        const char* e = getenv("GBXQ_TMA_L2PROMO");
+        return e ? atoi(e) : 256;
+    }();
+    const CUtensorMapL2promotion pr = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                      : (promo == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                                     : (promo == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
+    return enc(tm, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, pr,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 struct Maps {

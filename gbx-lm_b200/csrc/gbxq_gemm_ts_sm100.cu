@@ -18,6 +18,8 @@
 //   * x and packed weights have a producer warp each (x waits for the previous kernel of the stream -- programmatic
 //     dependent launch --, weights and scales are immutable and stream ahead of it);
 //   * split-K over blockIdx.z for skinny batches exactly as in gbxq_gemm_sm100.cu (deterministic reduction order).
+#include <cstdlib>
+
 #include "gbxq_umma.cuh"
 
 namespace gbxq {
@@ -50,6 +52,9 @@ struct TsParams {
     float* ws;
     uint32_t* cnt;
     int early_w;               // 1: weights / scales are immutable while the call is in flight: fetch before griddepcontrol.wait
+    const uint8_t* w_raw;      // packed weights (for the L2 prefetch of the CTA's rows)
+    int64_t row_bytes;
+    int l2_prefetch;           // > 0: the weight producer first asks L2 for this CTA's 128 rows in contiguous pieces
 };
 
 template <int BITS, int BN> struct Cfg {
@@ -202,6 +207,25 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         // ===================== packed-weight / scale producer =====================
         if (lane == 0) {
             if (!p.early_w) griddep_wait();
+            if (p.l2_prefetch > 0) {
+                // HBM -> L2 in long contiguous runs (the 128 rows of a tile are one contiguous block of the matrix); the
+                // tile loads below then gather their 64-byte row pieces from L2
+                const int64_t rows = min((int64_t)kTileN, p.N - n0);
+                const int64_t off = (int64_t)st_lo * (16 * BITS), len = (int64_t)nst * (16 * BITS);
+                if (len == p.row_bytes) {
+                    const uint8_t* base = p.w_raw + (int64_t)n0 * p.row_bytes;
+                    const int64_t total = rows * p.row_bytes;
+                    for (int64_t o = 0; o < total; o += 32768) {
+                        const uint32_t sz = (uint32_t)min((int64_t)32768, total - o);
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + o), "r"(sz) : "memory");
+                    }
+                } else {
+                    for (int64_t rr = 0; rr < rows; rr++)
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.w_raw + (n0 + rr) * p.row_bytes + off),
+                                     "r"((uint32_t)len)
+                                     : "memory");
+                }
+            }
             for (int s = 0; s < nst; s++) {
                 if (s % st_per_s == 0) {
                     const int sl = s / st_per_s, ss = sl % SS;
@@ -249,21 +273,24 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         const uint32_t wring_u32 = smem_u32(wring), sring_u32 = smem_u32(sring);
         const uint32_t a_lane = tmem_base + kTmemAOff + ((uint32_t)(rq * 32) << 16) + (uint32_t)(kq * 16);
         uint4 sreg = make_uint4(0u, 0u, 0u, 0u), breg = sreg;
-
-        for (int s = 0; s < nst; s++) {
+        // Software pipeline over the stages: the tcgen05.st of stage s is only waited for (and the stage handed to the
+        // MMA warp) after the ALU work of stage s+1, and the packed words of stage s+1 are fetched from shared memory
+        // while the store of stage s is in flight -- a warp's per-stage latency chain is its ~80 ALU instructions, not
+        // load + ALU + store round trip (r02r: 0.8 us per stage with the serial chain).
+        uint32_t w[BITS];
+        auto fetch = [&](int s) {
             const int ws = s % WS;
             mbar_wait(&wfull[ws], (uint32_t)(s / WS) & 1u);
-            uint32_t w[BITS];
             load_codes<BITS>(wring_u32 + (uint32_t)ws * C::W_SLOT, r, kq, w);
-            const bool new_slot = (s % st_per_s) == 0;
-            int ss = 0;
-            if (new_slot) {
-                const int sl = s / st_per_s;
-                ss = sl % SS;
+            if ((s % st_per_s) == 0) {
+                const int sl = s / st_per_s, ss = sl % SS;
                 mbar_wait(&sfull[ss], (uint32_t)(sl / SS) & 1u);
                 sreg = lds128(sring_u32 + (uint32_t)ss * C::S_SLOT + (uint32_t)r * 16u);
                 breg = lds128(sring_u32 + (uint32_t)ss * C::S_SLOT + kTileN * 16u + (uint32_t)r * 16u);
             }
+        };
+        if (nst > 0) fetch(0);
+        for (int s = 0; s < nst; s++) {
             const int gl = ((((st_lo + s) * kStageK) + kq * 32) >> p.gs_shift) & 7;  // group inside the 8-group slot
             const uint32_t sraw = pick16(sreg, gl), braw = pick16(breg, gl);
             uint32_t v[16];
@@ -273,18 +300,29 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 dequant8<BITS, BITS>(w, c, sraw, braw, o);
                 v[4 * c] = o[0]; v[4 * c + 1] = o[1]; v[4 * c + 2] = o[2]; v[4 * c + 3] = o[3];
             }
+            if (s > 0) {  // stage s-1: its store has had the whole dequantisation above to complete
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_a[(s - 1) % AS]);
+            }
             const int sa = s % AS;
             mbar_wait(&empty_a[sa], ((uint32_t)(s / AS) & 1u) ^ 1u);  // the MMAs that read this stage have retired
             tc_fence_after();
             tmem_st16(a_lane + (uint32_t)(sa * 64), v);
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&wempty[s % WS]);                 // the packed words of stage s were consumed above
+                if ((s % st_per_s) == st_per_s - 1 || s == nst - 1)
+                    mbar_arrive(&sempty[(s / st_per_s) % SS]);  // ... and so were the slot's scales after its last stage
+            }
+            if (s + 1 < nst) fetch(s + 1);
+        }
+        if (nst > 0) {
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&full_a[sa]);
-                mbar_arrive(&wempty[ws]);           // the packed words were consumed above
-                if (new_slot) mbar_arrive(&sempty[ss]);
-            }
+            if (lane == 0) mbar_arrive(&full_a[(nst - 1) % AS]);
         }
 
         // ---- epilogue: TMEM -> registers -> bf16 -> y[m, n]; warp drains its lane quarter and column quarter
@@ -432,6 +470,13 @@ int launch_gemm_ts(const void* x, const uint32_t* w, const void* s, const void* 
     p.gs_shift = gs == 32 ? 5 : (gs == 64 ? 6 : 7);
     p.splits = 1;
     p.early_w = mmv_get_pdl_mode() >= 2 ? 1 : 0;
+    p.w_raw = reinterpret_cast<const uint8_t*>(w);
+    p.row_bytes = K * bits / 8;
+    static const int l2pf = [] {
+        const char* e = getenv("GBXQ_TS_L2_PREFETCH");
+        return e ? atoi(e) : 0;
+    }();
+    p.l2_prefetch = l2pf;
     {
         int sp, per;
         size_t need;

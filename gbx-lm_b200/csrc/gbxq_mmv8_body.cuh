@@ -440,7 +440,9 @@ __device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, ui
         uint32_t bofs[NGL];  // byte offset of the lane's bias entries inside a stage (dead entries: x sum = 0, offset 0)
 #pragma unroll
         for (int i = 0; i < NGL; i++) {
-            const int idx = bq * NGL + i;
+            // R = 16 (two lanes per row): strided groups and separately rounded products below reproduce the summation
+            // tree of the R = 8 geometry bit for bit (single, grouped and chain launches must agree)
+            const int idx = R == 16 ? bq + i * LPR : bq * NGL + i;
             const int c = cwi + (idx / S) * p.cw;
             const bool on = idx < CPW * S && c < p.nch;
 #pragma unroll
@@ -527,7 +529,8 @@ __device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, ui
             for (int i = 0; i < NGL; i++) {
                 const float bv = lds_bf16(sslot + bofs[i]);
 #pragma unroll
-                for (int m = 0; m < MT; m++) bacc[m] = fmaf(bv, xg[i][m], bacc[m]);
+                for (int m = 0; m < MT; m++)
+                    bacc[m] = R == 16 ? __fadd_rn(bacc[m], __fmul_rn(bv, xg[i][m])) : fmaf(bv, xg[i][m], bacc[m]);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);  // slot free: all of this warp's shared-memory reads are done

@@ -170,6 +170,10 @@ def _qmm_grouped_op(
     if not x2.is_contiguous():
         x2 = x2.contiguous()
     m = x2.shape[0]
+    if m > 2:
+        # more rows than the one-launch decode kernel takes: one call per segment, each with its split-K scratch
+        # (gbxq_qmm_grouped's own per-segment fallback has none)
+        return [_qmm_impl(x, ws[i], scales[i], biases[i], bias[i], group_sizes[i], bits[i], 0) for i in range(nseg)]
     segs = (_lib.Segment * max(nseg, 1))()
     outs, keep = [], []
     for i in range(nseg):
@@ -234,12 +238,136 @@ def quantized_matmul(
     bias: Optional[torch.Tensor] = None,
     kernel: str = "auto",
 ) -> torch.Tensor:
-    """Drop-in for `mx.quantized_matmul` as QuantizedLinear calls it (transpose=True only; the
-    transpose=False form is used by the out-of-scope quantized-KV attention, models/base.py:85-93).
-    `bias` fuses QuantizedLinear's `x + bias` (quantized_linear_gba.py:204-205)."""
-    if not transpose:
-        raise NotImplementedError("quantized_matmul(transpose=False) is outside the QuantizedLinear path")
-    return _qmm_op(x, w, scales, biases, bias, int(group_size), int(bits), _KERNELS[kernel])
+    """Drop-in for `mx.quantized_matmul`.  2-D weights with transpose=True are the QuantizedLinear call
+    (quantized_linear_gba.py:195-203; `bias` fuses its `x + bias`, :204-205).  transpose=False (weights [.., K, N*bits/32]
+    quantized along N) and weights with leading batch dimensions are the quantized-KV attention forms
+    (gbx_lm/models/base.py:85-93): batch dimensions broadcast like a matmul's and run through `gbxq_gather_qmm`."""
+    if transpose and w.dim() == 2:
+        return _qmm_op(x, w, scales, biases, bias, int(group_size), int(bits), _KERNELS[kernel])
+    if bias is not None:
+        raise ValueError("[quantized_matmul] bias is fused for the 2-D transpose=True form only")
+    return _qmm_batched(x, w, scales, biases, bool(transpose), int(group_size), int(bits))
+
+
+def _gather_call(x3, w3, s3, b3, bias2, lhs, rhs, r: int, transpose: bool, group_size: int, bits: int) -> torch.Tensor:
+    """x3 [XB, M, K]; w3 [E, N, K*bits/32] (transpose) or [E, K, N*bits/32]; lhs / rhs int32 device tensors of r entries or
+    None (identity); returns [r, M, N]."""
+    _require_cuda(x3, w3, s3, b3, bias2, lhs, rhs)
+    _as_u32_ptr_tensor(w3)
+    if bits not in (2, 3, 4, 6, 8):
+        raise ValueError(f"[gather_qmm] bits must be one of 2, 3, 4, 6, 8; got {bits}")
+    if group_size not in (32, 64, 128):
+        raise ValueError(f"[gather_qmm] group_size must be 32, 64 or 128; got {group_size}")
+    if x3.dtype != s3.dtype or s3.dtype != b3.dtype or s3.shape != b3.shape:
+        raise ValueError("[gather_qmm] x, scales and biases must share a dtype; scales.shape == biases.shape")
+    xb, m, k = x3.shape
+    e = w3.shape[0]
+    quant = w3.shape[2] * 32 // bits          # length of the quantized (last) axis
+    if (w3.shape[2] * 32) % bits or s3.shape[0] != e or s3.shape[1] != w3.shape[1] or s3.shape[2] * group_size != quant:
+        raise ValueError(f"[gather_qmm] shapes disagree: qweight {tuple(w3.shape)} bits={bits}, scales {tuple(s3.shape)} group_size={group_size}")
+    if transpose:
+        n = w3.shape[1]
+        if quant != k:
+            raise ValueError(f"[gather_qmm] x last dim {k} != K {quant}")
+    else:
+        n = quant
+        if w3.shape[1] != k:
+            raise ValueError(f"[gather_qmm] x last dim {k} != K {w3.shape[1]}")
+    if bias2 is not None and (not transpose or bias2.shape != (e, n) or bias2.dtype != x3.dtype):
+        raise ValueError("[gather_qmm] bias must be [E, N] in the activation dtype (transpose=True only)")
+    x3, w3, s3, b3 = x3.contiguous(), w3.contiguous(), s3.contiguous(), b3.contiguous()
+    y = torch.empty((r, m, n), dtype=x3.dtype, device=x3.device)
+    with torch.cuda.device(x3.device):
+        st = torch.cuda.current_stream().cuda_stream
+        rc = _lib.get().gbxq_gather_qmm(
+            x3.data_ptr(), w3.data_ptr(), s3.data_ptr(), b3.data_ptr(), bias2.contiguous().data_ptr() if bias2 is not None else None,
+            lhs.data_ptr() if lhs is not None else None, rhs.data_ptr() if rhs is not None else None, y.data_ptr(),
+            r, xb, e, m, n, k, 1 if transpose else 0, bits, group_size, _dt(x3), st,
+        )
+    _lib.check(rc, "gbxq_gather_qmm")
+    return y
+
+
+def _batch_index(shape, out_shape, device) -> Optional[torch.Tensor]:
+    """int32 map from the flattened broadcast batch `out_shape` to the flattened batch `shape` (None = identity)."""
+    n = 1
+    for d in shape:
+        n *= d
+    if tuple(shape) == tuple(out_shape):
+        return None
+    idx = torch.arange(n, dtype=torch.int32, device=device).reshape(shape)
+    return idx.expand(out_shape).reshape(-1).contiguous()
+
+
+def _qmm_batched(x, w, scales, biases, transpose: bool, group_size: int, bits: int) -> torch.Tensor:
+    if w.dim() < 2 or x.dim() < 1 or scales.dim() != w.dim() or biases.shape != scales.shape:
+        raise ValueError("[quantized_matmul] qweight / scales / biases rank mismatch")
+    squeeze = x.dim() == 1
+    if squeeze:
+        x = x.unsqueeze(0)
+    xbat, wbat = tuple(x.shape[:-2]), tuple(w.shape[:-2])
+    if tuple(scales.shape[:-2]) != wbat:
+        raise ValueError("[quantized_matmul] scales batch dimensions differ from qweight's")
+    out_bat = tuple(torch.broadcast_shapes(xbat, wbat))
+    r = 1
+    for d in out_bat:
+        r *= d
+    x3 = x.reshape(-1, x.shape[-2], x.shape[-1])
+    w3 = w.reshape(-1, w.shape[-2], w.shape[-1])
+    s3 = scales.reshape(-1, scales.shape[-2], scales.shape[-1])
+    b3 = biases.reshape(-1, biases.shape[-2], biases.shape[-1])
+    # align the batch ranks before broadcasting the index maps
+    pad = lambda b: (1,) * (len(out_bat) - len(b)) + b  # noqa: E731
+    lhs = _batch_index(pad(xbat), out_bat, x.device)
+    rhs = _batch_index(pad(wbat), out_bat, x.device)
+    y = _gather_call(x3, w3, s3, b3, None, lhs, rhs, r, transpose, group_size, bits)
+    y = y.reshape(*out_bat, y.shape[-2], y.shape[-1])
+    return y.squeeze(-2) if squeeze else y
+
+
+def gather_qmm(
+    x: torch.Tensor,
+    w: torch.Tensor,
+    scales: torch.Tensor,
+    biases: torch.Tensor,
+    lhs_indices: Optional[torch.Tensor] = None,
+    rhs_indices: Optional[torch.Tensor] = None,
+    transpose: bool = True,
+    group_size: int = 64,
+    bits: int = 4,
+    *,
+    sorted_indices: bool = False,
+    bias: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    """Drop-in for `mx.gather_qmm` as QuantizedSwitchLinear calls it (gbx_lm/models/switch_layers.py:78-92):
+    x [..., M, K], w [E, N, K*bits/32] (a stack of experts; any leading batch shape), indices select the batch item of x
+    (lhs, default: x's own batch broadcast against the indices) and the expert (rhs) per output batch item.  The result
+    has shape broadcast(lhs_indices, rhs_indices).shape + [M, N].  `sorted_indices` is a scheduling hint in MLX; results
+    do not depend on it.  `bias` ([E, N]) fuses the layer's `x + bias[indices]` (switch_layers.py:89-90)."""
+    if w.dim() < 3:
+        raise ValueError("[gather_qmm] qweight must be a stack of matrices [..., E, N, K*bits/32]")
+    dev = x.device
+    xbat, wbat = tuple(x.shape[:-2]), tuple(w.shape[:-2])
+    nx = 1
+    for d in xbat:
+        nx *= d
+    ne = 1
+    for d in wbat:
+        ne *= d
+    if rhs_indices is None:
+        rhs_indices = torch.arange(ne, dtype=torch.int32, device=dev).reshape(wbat)
+    if lhs_indices is None:
+        lhs_indices = torch.arange(nx, dtype=torch.int32, device=dev).reshape(xbat)
+    out_bat = tuple(torch.broadcast_shapes(tuple(lhs_indices.shape), tuple(rhs_indices.shape)))
+    lhs = lhs_indices.to(device=dev, dtype=torch.int32).expand(out_bat).reshape(-1).contiguous()
+    rhs = rhs_indices.to(device=dev, dtype=torch.int32).expand(out_bat).reshape(-1).contiguous()
+    x3 = x.reshape(-1, x.shape[-2], x.shape[-1])
+    w3 = w.reshape(-1, w.shape[-2], w.shape[-1])
+    s3 = scales.reshape(-1, scales.shape[-2], scales.shape[-1])
+    b3 = biases.reshape(-1, biases.shape[-2], biases.shape[-1])
+    bias2 = bias.reshape(-1, bias.shape[-1]) if bias is not None else None
+    y = _gather_call(x3, w3, s3, b3, bias2, lhs, rhs, lhs.numel(), bool(transpose), int(group_size), int(bits))
+    return y.reshape(*out_bat, y.shape[-2], y.shape[-1])
 
 
 def quantized_matmul_grouped(x: torch.Tensor, layers: Sequence) -> List[torch.Tensor]:

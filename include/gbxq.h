@@ -231,6 +231,23 @@ int gbxq_silu_mul(const void* gate, const void* up, void* out, int64_t n, void* 
  * Returns GBXQ_EUNSUPPORTED (nothing enqueued) for other arguments: use the framework's dense matmul then.
  */
 int gbxq_head_gemv(const void* x, const void* weight, void* y, int64_t M, int64_t V, int64_t K, int dtype, void* stream);
+
+/*
+ * Index-batched quantized matmul, the two forms either side of the QuantizedLinear path:
+ *   transpose = 1:  y[r] = x[lhs[r]] . dequant(qweight[rhs[r]])^T (+ bias[rhs[r]])      -- mx.gather_qmm(x, w, scales,
+ *                   biases, rhs_indices=indices, transpose=True) of QuantizedSwitchLinear.__call__
+ *                   (gbx_lm/models/switch_layers.py:78-92); qweight [E, N, K*bits/32], scales / biases [E, N, K/gs],
+ *                   bias [E, N] or NULL.
+ *   transpose = 0:  y[r] = x[lhs[r]] . dequant(qweight[rhs[r]])                          -- mx.quantized_matmul(scores,
+ *                   *q_values, transpose=False) of the quantized KV cache attention (gbx_lm/models/base.py:90-92);
+ *                   qweight [E, K, N*bits/32] quantized along N, scales / biases [E, K, N/gs]; bias must be NULL.
+ * x is [XB, M, K], y is [R, M, N]; lhs_indices / rhs_indices are DEVICE int32 arrays of R entries (NULL = the identity
+ * r -> r); out-of-range indices are clamped into [0, XB) / [0, E).  transpose = 1 needs K % 32 == 0 and
+ * K % group_size == 0, transpose = 0 needs the same of N.  All dtypes (0 bf16, 1 f16, 2 f32), every width.
+ */
+int gbxq_gather_qmm(const void* x, const uint32_t* qweight, const void* scales, const void* biases, const void* bias,
+                    const int32_t* lhs_indices, const int32_t* rhs_indices, void* y, int64_t R, int64_t XB, int64_t E,
+                    int64_t M, int64_t N, int64_t K, int transpose, int bits, int group_size, int dtype, void* stream);
 /*
  * Tensor-parallel row-parallel epilogue (new work; the reference has no TP -- SURVEY.md 2.2):
  * one-shot sum all-reduce of a small [count] T vector over peer-mapped buffers on NVLink

@@ -294,6 +294,56 @@ def quantized_matmul(
 
 
 # ----------------------------------------------------------------------------------------
+# quantized_matmul(transpose=False) and gather_qmm  (oracle/MLX_SPEC.md section 5)
+# ----------------------------------------------------------------------------------------
+
+
+def _affine_f64(w, s, b, group_size: int, bits: int) -> np.ndarray:
+    """Exact affine matrix scale*q+bias in fp64 along the LAST (quantized) axis; any leading dimensions."""
+    q = unpack_codes(np.asarray(w, dtype=np.uint32), bits).astype(np.float64)
+    return np.repeat(s, group_size, -1).astype(np.float64) * q + np.repeat(b, group_size, -1).astype(np.float64)
+
+
+def quantized_matmul_nt(x, w, scales, biases, group_size: int = 64, bits: int = 4, dtype: str = "bf16") -> np.ndarray:
+    """mx.quantized_matmul(x, w, scales, biases, transpose=False): y[..., m, n] = sum_k x[..., m, k] * W[..., k, n] with
+    W[..., k, :] = scales[..., k, n//gs] * q[..., k, n] + biases[..., k, n//gs] -- the matrix is quantized along its last
+    axis N (as `scores @ V` on the quantized cache uses it, gbx_lm/models/base.py:90-92).  Batch dimensions of x and w
+    broadcast like a matmul's.  Exact weights, fp64 accumulation, one rounding to `dtype` (the "truth")."""
+    xf = _as_f32(x, dtype).astype(np.float64)
+    s = _as_f32(scales, dtype)
+    b = _as_f32(biases, dtype)
+    W = _affine_f64(w, s, b, group_size, bits)  # [..., K, N]
+    if xf.shape[-1] != W.shape[-2]:
+        raise ValueError(f"[quantized_matmul] x last dim {xf.shape[-1]} != K {W.shape[-2]}")
+    return _round_to(np.matmul(xf, W), dtype)
+
+
+def gather_qmm(x, w, scales, biases, lhs_indices=None, rhs_indices=None, transpose: bool = True, group_size: int = 64,
+               bits: int = 4, dtype: str = "bf16", bias=None) -> np.ndarray:
+    """mx.gather_qmm as QuantizedSwitchLinear.__call__ uses it (gbx_lm/models/switch_layers.py:78-92): x [..., M, K],
+    w [..., N, K*bits/32] (transpose) a stack of matrices; output batch item i multiplies x.reshape(-1, M, K)[lhs[i]]
+    with the dequantised matrix w.reshape(-1, ...)[rhs[i]]; lhs / rhs broadcast against each other and default to the
+    operands' own flattened batches.  `bias` [E, N]: the layer's separately rounded `+ bias[indices]` (:89-90)."""
+    xf = _as_f32(x, dtype).astype(np.float64)
+    s = _as_f32(scales, dtype)
+    b = _as_f32(biases, dtype)
+    W = _affine_f64(w, s, b, group_size, bits)
+    x3 = xf.reshape(-1, xf.shape[-2], xf.shape[-1])
+    W3 = W.reshape(-1, W.shape[-2], W.shape[-1])
+    lhs = np.arange(x3.shape[0]).reshape(xf.shape[:-2]) if lhs_indices is None else np.asarray(lhs_indices)
+    rhs = np.arange(W3.shape[0]).reshape(W.shape[:-2]) if rhs_indices is None else np.asarray(rhs_indices)
+    lhs, rhs = np.broadcast_arrays(lhs, rhs)
+    A = x3[lhs.reshape(-1)]
+    B = W3[rhs.reshape(-1)]
+    y = np.matmul(A, np.swapaxes(B, -1, -2) if transpose else B)
+    y = _round_to(y, dtype)
+    if bias is not None:
+        bf = _as_f32(bias, dtype).astype(np.float64).reshape(-1, y.shape[-1])
+        y = _round_to(y.astype(np.float64) + bf[rhs.reshape(-1)][:, None, :], dtype)
+    return y.reshape(*lhs.shape, y.shape[-2], y.shape[-1])
+
+
+# ----------------------------------------------------------------------------------------
 # quantize  (mx.quantize; only used to fabricate test weights -- SURVEY.md 8c.5.  The product
 # never needs to match it; kept for from_linear-style tests.)
 # ----------------------------------------------------------------------------------------

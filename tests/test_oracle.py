@@ -283,3 +283,70 @@ def test_indep_rne_matches_hardware_formats():
         want = A.bf16_bits_to_f32(A.f32_to_bf16_bits(np.array([np.float32(val)])))[0]
         # bf16 from the fp64 value directly vs via fp32: identical unless the fp32 step itself lands on a tie
         assert float(I.rne(Fraction(float(np.float32(val))), "bf16")) == float(want)
+
+
+# ---------------------------------------------------------------------------------- transpose=False / gather_qmm (8f-3, 8f-4)
+def _stack(E, N, K, bits, gs, seed):
+    Ls = [A.synth_layer(N, K, bits, gs, seed=seed + e) for e in range(E)]
+    return {k: np.stack([L[k] for L in Ls]) for k in ("qweight", "scales", "zeros")}
+
+
+@pytest.mark.parametrize("bits", A.SUPPORTED_BITS)
+def test_qmm_transpose_false_element_by_element(bits):
+    """x @ W with W quantized along its LAST axis: a pure-Python triple loop over the unpacked codes (no shared code
+    with the vectorised restatement beyond unpack_codes, itself checked above), bf16 scales."""
+    gs, K, N, M = 32, 5, 64, 3
+    L = A.synth_layer(K, N, bits, gs, seed=bits)           # rows = k, quantized axis = n
+    x = A.synth_x(M, K, seed=9)
+    y = A.quantized_matmul_nt(x, L["qweight"], L["scales"], L["zeros"], gs, bits, "bf16")
+    q = A.unpack_codes(L["qweight"], bits)
+    s, b, xf = A.bf16_bits_to_f32(L["scales"]), A.bf16_bits_to_f32(L["zeros"]), A.bf16_bits_to_f32(x)
+    for m in range(M):
+        for n in range(N):
+            acc = 0.0
+            for k in range(K):
+                acc += float(xf[m, k]) * (float(s[k, n // gs]) * int(q[k, n]) + float(b[k, n // gs]))
+            want = A.bf16_bits_to_f32(A.f32_to_bf16_bits(np.float32(acc)))
+            assert y[m, n] == want or abs(y[m, n] - want) <= 2.0 ** -7 * abs(want)  # fp64 sum order may move a tie
+
+
+def test_qmm_transpose_false_broadcasts_like_gqa_attention():
+    """scores [B, kv, rep, L, T] @ V codes [B, kv, 1, T, D]: the expanded-heads call of models/base.py:80-92."""
+    B, kv, rep, Lq, T, D, bits, gs = 2, 2, 3, 2, 7, 64, 8, 64
+    Ls = [A.synth_layer(T, D, bits, gs, seed=40 + i) for i in range(B * kv)]
+    pk = {k: np.stack([L[k] for L in Ls]).reshape(B, kv, 1, T, -1) for k in ("qweight", "scales", "zeros")}
+    x = A.synth_x(B * kv * rep * Lq, T, seed=3).reshape(B, kv, rep, Lq, T)
+    y = A.quantized_matmul_nt(x, pk["qweight"], pk["scales"], pk["zeros"], gs, bits, "bf16")
+    assert y.shape == (B, kv, rep, Lq, D)
+    for b in range(B):
+        for h in range(kv):
+            L = Ls[b * kv + h]
+            Wd = A.dequantize(L["qweight"], L["scales"], L["zeros"], gs, bits, "bf16")  # bf16-rounded weights: loose bound
+            ref = A.bf16_bits_to_f32(x[b, h]).astype(np.float64) @ Wd.astype(np.float64)
+            assert np.abs(y[b, h] - ref).max() <= 2.0 ** -6 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("bits", (2, 3, 4, 6, 8))
+def test_gather_qmm_is_indexed_quantized_matmul(bits):
+    """gather_qmm == quantized_matmul of the selected (x row block, expert) pairs; indices broadcast; bias per expert."""
+    E, N, K, gs = 5, 24, 64, 32
+    st = _stack(E, N, K, bits, gs, seed=bits)
+    rng = np.random.default_rng(bits)
+    bias = A.f32_to_bf16_bits(rng.standard_normal((E, N)).astype(np.float32))
+    # the SwitchGLU call shape: x [T, 1, 1, K] against indices [T, topk] (switch_layers.py:181-196)
+    T, topk = 6, 3
+    x = A.synth_x(T, K, seed=1).reshape(T, 1, 1, K)
+    idx = rng.integers(0, E, size=(T, topk))
+    lhs = np.arange(T).reshape(T, 1)
+    y = A.gather_qmm(x, st["qweight"], st["scales"], st["zeros"], lhs, idx, True, gs, bits, "bf16", bias=bias)
+    assert y.shape == (T, topk, 1, N)
+    for t in range(T):
+        for j in range(topk):
+            e = idx[t, j]
+            ref = A.quantized_matmul(x[t, 0], st["qweight"][e], st["scales"][e], st["zeros"][e], gs, bits, "bf16", "f64", bias=bias[e])
+            assert np.array_equal(y[t, j], ref)
+    # default indices: batch item i of x against matrix i of w
+    x2 = A.synth_x(E * 2, K, seed=2).reshape(E, 2, K)
+    y2 = A.gather_qmm(x2, st["qweight"], st["scales"], st["zeros"], None, None, True, gs, bits, "bf16")
+    for e in range(E):
+        assert np.array_equal(y2[e], A.quantized_matmul(x2[e], st["qweight"][e], st["scales"][e], st["zeros"][e], gs, bits, "bf16", "f64"))
