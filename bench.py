@@ -468,7 +468,7 @@ def run_gbxq(args):
         line["prefill_tok_s_qmm_only"] = round(M * replicas / (ms_step * 1e-3), 1)
         ach = rank_flops / (ms_step * 1e-3) / 1e12
         line["roofline"] = {"bound": "tensor", "achieved": round(ach, 2), "peak": tpeak, "unit": "TFLOP/s", "frac": round(ach / tpeak, 4),
-                            "traffic": None, "peak_source": tsrc, "kernel": "gbxq::gemm_kernel (tcgen05.mma swap-AB, in-kernel dequant)",
+                            "traffic": None, "peak_source": tsrc, "kernel": "gbxq::gemm_ts_kernel (tcgen05.mma swap-AB, dequantised weights as the TMEM operand)",
                             "flops_per_launch_avg": rank_flops / max(launches_per_step, 1),
                             "avg_launch_us": round(ms_step * 1e3 / max(launches_per_step, 1), 3)}
         line["e2e"]["value"] = round(flops / (e2e_ms * 1e-3) / 1e12, 2)

@@ -32,10 +32,12 @@ static constexpr int64_t kMmvMaxM = 2;
 static constexpr int64_t kSkinnyMaxM = 16;  // 2 passes of 8 tokens; above that the tcgen05 GEMM amortises better
 
 // Rows of x from which the TMEM-operand GEMM (gbxq_gemm_ts_sm100.cu) takes over (GBXQ_TS_MIN_M overrides; 0 = never).
+// Measured on the 8B decode step (profiles/r02y_*): 8 rows 2.09 ms on the skinny kernel against 3.22 ms, 16 rows 3.9
+// against 3.28 ms, 32 rows 5.9 (shared-memory-operand GEMM) against 3.76 ms -> from 9 rows.
 static int ts_min_m() {
     static const int v = [] {
         const char* e = getenv("GBXQ_TS_MIN_M");
-        return e ? atoi(e) : 0;
+        return e ? atoi(e) : 9;
     }();
     return v;
 }
@@ -96,6 +98,9 @@ void gbxq_debug_timeline(unsigned long long* buf_dev, int launches) { mmv8_debug
 void gbxq_debug_timeline_all(unsigned long long* buf_dev, int launches, int stride_ctas) {
     mmv8_debug_timeline_all(buf_dev, launches, stride_ctas);
 }
+
+// Development aid: the NEXT GBXQ_KERNEL_GEMM_TS launch writes its CTA-0 timeline (8 + 4 * 64 slots) to buf_dev.
+void gbxq_debug_ts_timeline(unsigned long long* buf_dev) { gemm_ts_debug_timeline(buf_dev); }
 
 void gbxq_debug_stream_timeline(void* host_blob, int ncalls, unsigned long long* dbg_dev) {
     stream_debug_patch(host_blob, ncalls, dbg_dev);

@@ -32,13 +32,17 @@ namespace {
 
 using namespace umma;
 
-constexpr int kStageK = 128;   // k per stage = 64 TMEM columns of A = 2 x tiles ("atoms") of 64 k
+constexpr int kHalfK = 128;    // one TMA box of packed codes: 128 rows x 128 codes
+constexpr int kH = 2;          // boxes ("halves") per stage: the per-stage barrier traffic of the dequant warps (~120 of
+                               // their ~195 instructions per 128 k, r02x SASS) is paid once per 256 k
+constexpr int kStageK = kHalfK * kH;  // k per stage = 128 TMEM columns of A = 4 x tiles ("atoms") of 64 k
 constexpr int kAtomK = 64;
 constexpr int kTileN = 128;    // output features per CTA (= UMMA M = TMEM lanes)
 constexpr int kDqWarps = 16;   // warps 1..16: (row quarter = warp % 4, k quarter = (warp - 1) / 4)
 constexpr int kWarpMma = 17, kWarpW = 18;
 constexpr int kThreads = 19 * 32;
-constexpr int kAStages = 4;
+constexpr int kAStages = 2;
+constexpr int kAtomsPerStage = kStageK / 64;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTmemAOff = 256;
 constexpr size_t kCntBytes = 16384;  // counter header of the split-K workspace (as gbxq_gemm_sm100.cu)
@@ -54,24 +58,43 @@ struct TsParams {
     int early_w;               // 1: weights / scales are immutable while the call is in flight: fetch before griddepcontrol.wait
     const uint8_t* w_raw;      // packed weights (for the L2 prefetch of the CTA's rows)
     int64_t row_bytes;
-    int l2_prefetch;           // > 0: the weight producer first asks L2 for this CTA's 128 rows in contiguous pieces
+    int rotate;                // 1: CTAs start their k loop at different stages (see stage_of)
+    unsigned long long* dbg;   // development aid (gbxq_debug_ts_timeline): CTA 0 stamps %globaltimer, see tools/ts_timeline.py
 };
 
 template <int BITS, int BN> struct Cfg {
-    static constexpr int XS = BN == 256 ? 5 : 8;                    // x atoms in flight (2 per stage)
+    static constexpr int XS = BN == 256 ? (BITS >= 8 ? 4 : 5) : 8;  // x atoms in flight (4 per stage)
     static constexpr uint32_t B_BYTES = BN * kAtomK * 2;
     static constexpr uint32_t W_ROW = 16 * BITS;                    // packed bytes of 128 codes
-    static constexpr uint32_t W_SLOT = kTileN * W_ROW;              // 2*BITS KB
+    static constexpr uint32_t W_HALF = kTileN * W_ROW;              // 2*BITS KB: one TMA box
+    static constexpr uint32_t W_SLOT = kH * W_HALF;
     static constexpr int WS_RAW = (48 * 1024) / W_SLOT;
-    static constexpr int WS = WS_RAW > 8 ? 8 : (WS_RAW < 3 ? 3 : WS_RAW);
+    static constexpr int WS = WS_RAW > 8 ? 8 : (WS_RAW < 2 ? 2 : WS_RAW);
     static constexpr uint32_t S_SLOT = 2 * kTileN * 16;             // scales + biases of 8 groups per row
     static constexpr int SS = 4;
+    // Independent accumulators: the K = 16 steps of a tile go round-robin to NACC accumulators (TMEM columns j * BN) that
+    // the epilogue adds in a fixed order.  A narrow MMA (N = 16: 8 clocks of tensor-pipe work) that accumulates into
+    // the columns its predecessor has just written waits for that write-back: r02u/r02v timelines show ~100 ns per
+    // dependent MMA, 0.8 us per 128-k stage whatever the width of the codes or the batch.
+    static constexpr int NACC = BN <= 64 ? 4 : (BN == 128 ? 2 : 1);
     static constexpr int NBAR = 2 * XS + 2 * WS + 2 * SS + 2 * kAStages + 1;
     static constexpr size_t SMEM = (size_t)XS * B_BYTES + (size_t)WS * W_SLOT + (size_t)SS * S_SLOT + NBAR * 8 + 16 + 1024;
 };
 
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// timeline layout (CTA 0 only): [0] entry, [1] set-up done, [2] epilogue start, [3] exit, then per stage s (s < 64):
+// [8 + 4s + 0] packed words landed (dequant warp 1), [.. + 1] A stage stored, [.. + 2] MMAs issued, [.. + 3] x tile landed
+#define TS_STAMP(i)                                                                                        \
+    do {                                                                                                   \
+        if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.dbg[(i)] = gtime(); \
+    } while (0)
 
 __device__ __forceinline__ uint32_t lds32(uint32_t a) {
     uint32_t v;
@@ -147,11 +170,23 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     const int n0 = blockIdx.x * kTileN;
     const int m0 = blockIdx.y * BN;
     const int st_all = (int)(p.K / kStageK);
-    const int st_lo = p.splits > 1 ? (int)blockIdx.z * (p.kb_per_split >> 1) : 0;    // first stage of this split
-    const int nst = p.splits > 1 ? min(p.kb_per_split >> 1, st_all - st_lo) : st_all;  // stages of this CTA
-    const int st_per_s = p.gs_shift == 5 ? 2 : (p.gs_shift == 6 ? 4 : 8);              // stages per scale slot (8 groups)
-    const int sl_lo = st_lo / st_per_s;
+    const int st_lo = p.splits > 1 ? (int)blockIdx.z * (p.kb_per_split >> 2) : 0;    // first stage of this split
+    const int nst = p.splits > 1 ? min(p.kb_per_split >> 2, st_all - st_lo) : st_all;  // stages of this CTA
+    const int sps_shift = p.gs_shift - 5;                                             // log2(stages per 8-group scale slot)
+    const int st_per_s = 1 << sps_shift;                                              // 1, 2, 4 for group sizes 32, 64, 128
+    const int sl_lo = st_lo >> sps_shift;
+    // Optional k rotation (GBXQ_TS_ROTATE=1): CTA b walks its stages starting at stage rot(b) and wraps around, so that
+    // the CTAs of a grid do not all ask L2 for the same x tile at the same time.  Measured (r02v-r02y): no gain at small
+    // batches (the loop is bound by the dequant warps' instruction issue, not by x) and -5 % on prefill tiles, where
+    // lock-step CTAs share their x tiles in L2 -- off by default.  The order is fixed per CTA either way: deterministic.
+    const int nrot = (p.rotate && nst % st_per_s == 0) ? nst / st_per_s : 1;
+    const int rot = (int)(blockIdx.x % (unsigned)nrot) * st_per_s;
+    auto stage_of = [&](int s) {  // loop index -> stage of this CTA's k range
+        const int t = s + rot;
+        return t >= nst ? t - nst : t;
+    };
 
+    if (threadIdx.x == 0) TS_STAMP(0);
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < XS; s++) {
@@ -191,79 +226,83 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) griddep_launch();  // the next kernel of the stream may start its prologue when SMs free up
+    if (threadIdx.x == 0) TS_STAMP(1);
 
+    // The three single-issuer roles below run their loops with the WHOLE warp (uniform control flow, every lane polls
+    // the barriers) and elect one lane per asynchronous instruction.  Written as `if (lane == 0) { loop }` each
+    // tcgen05.mma cost ~16 SASS instructions (ELECT / R2UR.BROADCAST loops around every operand): ~150 clocks per MMA,
+    // 0.77 us per 128-k stage -- the bound of r02r-r02w whatever the code width, the batch or the x / weight streams.
     if (warp == 0) {
         // ===================== x producer =====================
-        if (lane == 0) {
-            griddep_wait();  // x belongs to the previous kernels of the stream
-            for (int a = 0; a < 2 * nst; a++) {
-                const int s = a % XS;
-                mbar_wait(&empty_b[s], ((uint32_t)(a / XS) & 1u) ^ 1u);
+        griddep_wait();  // x belongs to the previous kernels of the stream
+        const uint32_t xring_u32 = smem_u32(xring);
+        for (int a = 0; a < kAtomsPerStage * nst; a++) {
+            const int s = a % XS;
+            mbar_wait(&empty_b[s], ((uint32_t)(a / XS) & 1u) ^ 1u);
+            if (elect_one()) {
                 mbar_arrive_expect_tx(&full_b[s], C::B_BYTES);
-                tma_load_2d(xring + (size_t)s * C::B_BYTES, &tmap_x, (2 * st_lo + a) * kAtomK, m0, &full_b[s]);
+                tma_load_2d_u32(xring_u32 + (uint32_t)s * C::B_BYTES, &tmap_x, (kAtomsPerStage * (st_lo + stage_of(a / kAtomsPerStage)) + (a % kAtomsPerStage)) * kAtomK, m0,
+                                smem_u32(&full_b[s]));
             }
+            __syncwarp();
         }
     } else if (warp == kWarpW) {
         // ===================== packed-weight / scale producer =====================
-        if (lane == 0) {
-            if (!p.early_w) griddep_wait();
-            if (p.l2_prefetch > 0) {
-                // HBM -> L2 in long contiguous runs (the 128 rows of a tile are one contiguous block of the matrix); the
-                // tile loads below then gather their 64-byte row pieces from L2
-                const int64_t rows = min((int64_t)kTileN, p.N - n0);
-                const int64_t off = (int64_t)st_lo * (16 * BITS), len = (int64_t)nst * (16 * BITS);
-                if (len == p.row_bytes) {
-                    const uint8_t* base = p.w_raw + (int64_t)n0 * p.row_bytes;
-                    const int64_t total = rows * p.row_bytes;
-                    for (int64_t o = 0; o < total; o += 32768) {
-                        const uint32_t sz = (uint32_t)min((int64_t)32768, total - o);
-                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + o), "r"(sz) : "memory");
-                    }
-                } else {
-                    for (int64_t rr = 0; rr < rows; rr++)
-                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.w_raw + (n0 + rr) * p.row_bytes + off),
-                                     "r"((uint32_t)len)
-                                     : "memory");
-                }
-            }
-            for (int s = 0; s < nst; s++) {
-                if (s % st_per_s == 0) {
-                    const int sl = s / st_per_s, ss = sl % SS;
-                    mbar_wait(&sempty[ss], ((uint32_t)(sl / SS) & 1u) ^ 1u);
+        if (!p.early_w) griddep_wait();
+        const uint32_t wring_b = smem_u32(wring), sring_b = smem_u32(sring);
+        for (int s = 0; s < nst; s++) {
+            if ((s & (st_per_s - 1)) == 0) {
+                const int sl = s >> sps_shift, ss = sl % SS;
+                mbar_wait(&sempty[ss], ((uint32_t)(sl / SS) & 1u) ^ 1u);
+                if (elect_one()) {
+                    const int gsl = sl_lo + (stage_of(s) >> sps_shift);  // the slot's place in the matrix
                     mbar_arrive_expect_tx(&sfull[ss], C::S_SLOT);
-                    tma_load_2d(sring + (size_t)ss * C::S_SLOT, &tmap_s, (sl_lo + sl) * 8, n0, &sfull[ss]);
-                    tma_load_2d(sring + (size_t)ss * C::S_SLOT + kTileN * 16, &tmap_b, (sl_lo + sl) * 8, n0, &sfull[ss]);
+                    tma_load_2d_u32(sring_b + (uint32_t)ss * C::S_SLOT, &tmap_s, gsl * 8, n0, smem_u32(&sfull[ss]));
+                    tma_load_2d_u32(sring_b + (uint32_t)ss * C::S_SLOT + kTileN * 16, &tmap_b, gsl * 8, n0, smem_u32(&sfull[ss]));
                 }
-                const int ws = s % WS;
-                mbar_wait(&wempty[ws], ((uint32_t)(s / WS) & 1u) ^ 1u);
-                mbar_arrive_expect_tx(&wfull[ws], C::W_SLOT);
-                tma_load_2d(wring + (size_t)ws * C::W_SLOT, &tmap_w, (st_lo + s) * 4 * BITS, n0, &wfull[ws]);
+                __syncwarp();
             }
+            const int ws = s % WS;
+            mbar_wait(&wempty[ws], ((uint32_t)(s / WS) & 1u) ^ 1u);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&wfull[ws], C::W_SLOT);
+#pragma unroll
+                for (int h = 0; h < kH; h++)
+                    tma_load_2d_u32(wring_b + (uint32_t)ws * C::W_SLOT + (uint32_t)h * C::W_HALF, &tmap_w,
+                                    ((st_lo + stage_of(s)) * kH + h) * 4 * BITS, n0, smem_u32(&wfull[ws]));
+            }
+            __syncwarp();
         }
     } else if (warp == kWarpMma) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(kTileN, BN);
-            for (int s = 0; s < nst; s++) {
-                const int sa = s % AS;
-                mbar_wait(&full_a[sa], (uint32_t)(s / AS) & 1u);
+        constexpr uint32_t idesc = make_idesc_bf16(kTileN, BN);
+        // K-major SWIZZLE_128B descriptor of an x tile: low word = address >> 4 | LBO(1) << 16, high word constant
+        constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+        const uint32_t xring_u32 = smem_u32(xring);
+        for (int s = 0; s < nst; s++) {
+            const int sa = s % AS;
+            mbar_wait(&full_a[sa], (uint32_t)(s / AS) & 1u);
 #pragma unroll
-                for (int a = 0; a < 2; a++) {
-                    const int ai = 2 * s + a, ax = ai % XS;
-                    mbar_wait(&full_b[ax], (uint32_t)(ai / XS) & 1u);
-                    tc_fence_after();
-                    const uint32_t b_addr = smem_u32(xring + (size_t)ax * C::B_BYTES);
-                    const uint32_t a_tmem = tmem_base + kTmemAOff + (uint32_t)(sa * 64 + a * 32);
+            for (int a = 0; a < kAtomsPerStage; a++) {
+                const int ai = kAtomsPerStage * s + a, ax = ai % XS;
+                mbar_wait(&full_b[ax], (uint32_t)(ai / XS) & 1u);
+                tc_fence_after();
+                const uint32_t b_lo = (((xring_u32 + (uint32_t)ax * C::B_BYTES) & 0x3FFFFu) >> 4) | (1u << 16);
+                const uint32_t a_tmem = tmem_base + kTmemAOff + (uint32_t)(sa * (kStageK / 2) + a * 32);
+                const uint32_t first = (s | a) != 0 ? 1u : 0u;
+                if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < kAtomK / 16; k++)
-                        mma_ts_f16(tmem_base, a_tmem + (uint32_t)(k * 8), make_sw128_kmajor_desc(b_addr + k * 32), idesc,
-                                   (s | a | k) != 0 ? 1u : 0u);
+                        mma_ts_f16_lohi(tmem_base + (uint32_t)((k % C::NACC) * BN), a_tmem + (uint32_t)(k * 8), b_lo + (uint32_t)(2 * k),
+                                        kDescHi, idesc, k >= C::NACC ? 1u : first);
                     mma_commit(&empty_b[ax]);   // the x tile is free once these MMAs retire
+                    if (a == kAtomsPerStage - 1) mma_commit(&empty_a[sa]);  // ... and so is the A stage
                 }
-                mma_commit(&empty_a[sa]);       // ... and so is the A stage
+                __syncwarp();
             }
-            mma_commit(tmem_full);              // accumulator complete -> epilogue
         }
+        if (elect_one()) mma_commit(tmem_full);  // accumulator complete -> epilogue
+        __syncwarp();
     } else {
         // ===================== dequant warps (1..16), then epilogue =====================
         const int dw = warp - 1;
@@ -277,56 +316,79 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         // MMA warp) after the ALU work of stage s+1, and the packed words of stage s+1 are fetched from shared memory
         // while the store of stage s is in flight -- a warp's per-stage latency chain is its ~80 ALU instructions, not
         // load + ALU + store round trip (r02r: 0.8 us per stage with the serial chain).
-        uint32_t w[BITS];
-        auto fetch = [&](int s) {
-            const int ws = s % WS;
-            mbar_wait(&wfull[ws], (uint32_t)(s / WS) & 1u);
-            load_codes<BITS>(wring_u32 + (uint32_t)ws * C::W_SLOT, r, kq, w);
-            if ((s % st_per_s) == 0) {
-                const int sl = s / st_per_s, ss = sl % SS;
-                mbar_wait(&sfull[ss], (uint32_t)(sl / SS) & 1u);
-                sreg = lds128(sring_u32 + (uint32_t)ss * C::S_SLOT + (uint32_t)r * 16u);
-                breg = lds128(sring_u32 + (uint32_t)ss * C::S_SLOT + kTileN * 16u + (uint32_t)r * 16u);
-            }
-        };
-        if (nst > 0) fetch(0);
-        for (int s = 0; s < nst; s++) {
-            const int gl = ((((st_lo + s) * kStageK) + kq * 32) >> p.gs_shift) & 7;  // group inside the 8-group slot
-            const uint32_t sraw = pick16(sreg, gl), braw = pick16(breg, gl);
-            uint32_t v[16];
+        // Ring positions advance by increments (no divisions in the loop): fetch side (f*) runs one stage ahead of the
+        // compute side (c*).  sin = stage inside its 8-group scale slot (the rotation keeps whole slots together).
+        uint32_t w[kH][BITS];
+        const int sps_mask = st_per_s - 1;
+        const int gl_shift = 8 - p.gs_shift;                 // groups per stage = 1 << gl_shift
+        int gl_base[kH];                                     // this thread's group inside the stage, per half
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-                uint32_t o[4];
-                dequant8<BITS, BITS>(w, c, sraw, braw, o);
-                v[4 * c] = o[0]; v[4 * c + 1] = o[1]; v[4 * c + 2] = o[2]; v[4 * c + 3] = o[3];
+        for (int h = 0; h < kH; h++) gl_base[h] = (h * kHalfK + kq * 32) >> p.gs_shift;
+        uint32_t f_w = wring_u32, f_s = sring_u32 + (uint32_t)r * 16u;
+        uint32_t f_wbar = smem_u32(wfull), f_sbar = smem_u32(sfull);
+        uint32_t f_wph = 0, f_sph = 0;
+        int f_ws = 0, f_ss = 0, f_sin = 0;
+        auto fetch = [&]() {
+            mbar_wait_u32(f_wbar + 8u * f_ws, f_wph);
+#pragma unroll
+            for (int h = 0; h < kH; h++) load_codes<BITS>(f_w + (uint32_t)f_ws * C::W_SLOT + (uint32_t)h * C::W_HALF, r, kq, w[h]);
+            if (f_sin == 0) {
+                mbar_wait_u32(f_sbar + 8u * f_ss, f_sph);
+                sreg = lds128(f_s + (uint32_t)f_ss * C::S_SLOT);
+                breg = lds128(f_s + (uint32_t)f_ss * C::S_SLOT + kTileN * 16u);
+                if (++f_ss == SS) { f_ss = 0; f_sph ^= 1u; }
+            }
+            f_sin = (f_sin + 1) & sps_mask;
+            if (++f_ws == WS) { f_ws = 0; f_wph ^= 1u; }
+        };
+        const uint32_t fa_bar = smem_u32(full_a), ea_bar = smem_u32(empty_a), we_bar = smem_u32(wempty), se_bar = smem_u32(sempty);
+        int c_ws = 0, c_ss = 0, c_sin = 0, c_sa = 0;
+        uint32_t c_aph = 1u;                                 // parity of "stage free" (fresh barriers pass a wait on 1)
+        if (nst > 0) fetch();
+        for (int s = 0; s < nst; s++) {
+            uint32_t v[kH][16];
+#pragma unroll
+            for (int h = 0; h < kH; h++) {
+                const int gl = (c_sin << gl_shift) + gl_base[h];  // group inside the 8-group slot
+                const uint32_t sraw = pick16(sreg, gl), braw = pick16(breg, gl);
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    uint32_t o[4];
+                    dequant8<BITS, BITS>(w[h], c, sraw, braw, o);
+                    v[h][4 * c] = o[0]; v[h][4 * c + 1] = o[1]; v[h][4 * c + 2] = o[2]; v[h][4 * c + 3] = o[3];
+                }
             }
             if (s > 0) {  // stage s-1: its store has had the whole dequantisation above to complete
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&full_a[(s - 1) % AS]);
+                if (lane == 0) mbar_arrive_u32(fa_bar + 8u * (uint32_t)((c_sa + AS - 1) & (AS - 1)));
             }
-            const int sa = s % AS;
-            mbar_wait(&empty_a[sa], ((uint32_t)(s / AS) & 1u) ^ 1u);  // the MMAs that read this stage have retired
+            mbar_wait_u32(ea_bar + 8u * c_sa, c_aph);        // the MMAs that read this stage have retired
             tc_fence_after();
-            tmem_st16(a_lane + (uint32_t)(sa * 64), v);
+#pragma unroll
+            for (int h = 0; h < kH; h++) tmem_st16(a_lane + (uint32_t)(c_sa * (kStageK / 2) + h * (kHalfK / 2)), v[h]);
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive(&wempty[s % WS]);                 // the packed words of stage s were consumed above
-                if ((s % st_per_s) == st_per_s - 1 || s == nst - 1)
-                    mbar_arrive(&sempty[(s / st_per_s) % SS]);  // ... and so were the slot's scales after its last stage
+                mbar_arrive_u32(we_bar + 8u * c_ws);         // the packed words of stage s were consumed above
+                if (c_sin == sps_mask || s == nst - 1) mbar_arrive_u32(se_bar + 8u * c_ss);  // ... and the slot's scales
             }
-            if (s + 1 < nst) fetch(s + 1);
+            if (c_sin == sps_mask) { if (++c_ss == SS) c_ss = 0; }
+            c_sin = (c_sin + 1) & sps_mask;
+            if (++c_ws == WS) c_ws = 0;
+            if (++c_sa == AS) { c_sa = 0; c_aph ^= 1u; }
+            if (s + 1 < nst) fetch();
         }
         if (nst > 0) {
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&full_a[(nst - 1) % AS]);
+            if (lane == 0) mbar_arrive_u32(fa_bar + 8u * (uint32_t)((c_sa + AS - 1) & (AS - 1)));
         }
 
         // ---- epilogue: TMEM -> registers -> bf16 -> y[m, n]; warp drains its lane quarter and column quarter
         mbar_wait(tmem_full, 0);
+        if (threadIdx.x == 32) TS_STAMP(2);
         tc_fence_after();
         griddep_wait();  // y may still be read by an earlier kernel of the stream
         const int er = rq * 32 + lane;
@@ -340,6 +402,13 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         for (int c0 = cq * QCOLS; c0 < (cq + 1) * QCOLS; c0 += STEP) {
             uint32_t v[32];
             tmem_ld<STEP>(tmem_base + ((uint32_t)(rq * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+            for (int j = 1; j < C::NACC; j++) {  // fixed order: deterministic
+                uint32_t u[32];
+                tmem_ld<STEP>(tmem_base + ((uint32_t)(rq * 32) << 16) + (uint32_t)(j * BN + c0), u);
+#pragma unroll
+                for (int i = 0; i < STEP; i++) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
+            }
             if (row_ok) {
 #pragma unroll
                 for (int j = 0; j < STEP; j++) {
@@ -384,6 +453,7 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         }
     }
     __syncthreads();
+    if (threadIdx.x == 0) TS_STAMP(3);
     if (warp == 0) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
@@ -431,14 +501,18 @@ int launch_bn(int bn, const Maps& mp, const TsParams& p, cudaStream_t st) {
     }
 }
 
+unsigned long long* g_ts_dbg = nullptr;
+
 int pick_bn(int64_t M) { return M <= 16 ? 16 : (M <= 32 ? 32 : (M <= 64 ? 64 : (M <= 128 ? 128 : 256))); }
 
 }  // namespace
 
+void gemm_ts_debug_timeline(unsigned long long* buf) { g_ts_dbg = buf; }
+
 bool gemm_ts_supported(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype, const void* x, const void* w,
                        const void* y) {
     if (dtype != GBXQ_BF16 || M < 1 || N < 1) return false;
-    if (K % kStageK) return false;
+    if (K % kStageK) return false;              // whole 256-k stages
     if ((K * bits / 8) % 16) return false;      // TMA: packed row pitch must be a multiple of 16 bytes
     if (((K / gs) * 2) % 16) return false;      // TMA: scale row pitch must be a multiple of 16 bytes
     if (((uintptr_t)x | (uintptr_t)w) & 15) return false;
@@ -472,11 +546,13 @@ int launch_gemm_ts(const void* x, const uint32_t* w, const void* s, const void* 
     p.early_w = mmv_get_pdl_mode() >= 2 ? 1 : 0;
     p.w_raw = reinterpret_cast<const uint8_t*>(w);
     p.row_bytes = K * bits / 8;
-    static const int l2pf = [] {
-        const char* e = getenv("GBXQ_TS_L2_PREFETCH");
+    static const int rotate = [] {
+        const char* e = getenv("GBXQ_TS_ROTATE");
         return e ? atoi(e) : 0;
     }();
-    p.l2_prefetch = l2pf;
+    p.rotate = rotate;
+    p.dbg = g_ts_dbg;
+    g_ts_dbg = nullptr;  // one launch
     {
         int sp, per;
         size_t need;

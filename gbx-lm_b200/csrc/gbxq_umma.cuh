@@ -17,6 +17,12 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0,
         "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_u32(uint32_t dst_smem, const void* tmap, int c0, int c1, uint32_t bar_smem) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(bar_smem)
+        : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
@@ -52,6 +58,34 @@ __device__ __forceinline__ void mma_ts_f16(uint32_t tmem_d, uint32_t tmem_a, uin
         "}\n" ::"r"(tmem_d),
         "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
+}
+// the same with the shared-memory descriptor as two 32-bit halves (the issue loop keeps them in uniform registers and
+// steps the low half by the K offset)
+__device__ __forceinline__ void mma_ts_f16_lohi(uint32_t tmem_d, uint32_t tmem_a, uint32_t bdesc_lo, uint32_t bdesc_hi,
+                                                uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 bd;\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "mov.b64 bd, {%2, %3};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// one lane of a converged warp (the others skip): keeps the surrounding control flow warp-uniform, so the compiler
+// holds addresses / descriptors in uniform registers instead of broadcasting them lane by lane
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
