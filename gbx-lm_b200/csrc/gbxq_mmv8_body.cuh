@@ -700,7 +700,9 @@ inline Plan make_plan(int64_t M, int64_t N, int64_t K, int bits, int gs, int gri
     static const int grid_mult = env_int("GBXQ_MMV8_GRID_MULT", 2 / kWide);
     static const int stage_kb = env_int("GBXQ_MMV8_STAGE_KB", 32 * kWide);
     static const int ring_kb = env_int("GBXQ_MMV8_RING_KB", 96 * kWide);
-    static const int two_cols_from = env_int("GBXQ_MMV8_TWOCOLS", kCW == 8 ? 8 : 32);
+    // r03a sweep (16 warps): two columns per warp from 16 columns (K = 4096 at gs 64: 0.52 of HBM on the 8B step against
+    // 0.46 with one column and 16-row stages), one column and 16-row stages below (K = 3072: 3B step 0.40 against 0.37)
+    static const int two_cols_from = env_int("GBXQ_MMV8_TWOCOLS", kCW == 8 ? 8 : 16);
     static const int r16 = env_int("GBXQ_MMV8_R16", kCW == 16 ? 1 : 0);
     // chunk columns per warp: the smallest power of two that covers the row with 8 warps, but at least 2 (two
     // independent MMA chains per set) when the row has 8 columns or more

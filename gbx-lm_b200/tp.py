@@ -142,8 +142,14 @@ class OneShotAllReduce:
         torch.cuda.synchronize(device)
         dist.barrier(self.group)
 
+    # The one-shot kernel is for the latency-bound decode messages (M*hidden*2 bytes: 16 KB .. 1 MB); a prefill chunk's
+    # 40 MB partial goes to NCCL's bandwidth-optimal rings (r03e: Qwen2.5-32B prefill of 4096 tokens at tp4 took 1165 ms
+    # with every message on the one-shot kernel, 5x the single-GPU time).
+    MAX_BYTES = 1 << 20
+
     def fits(self, y: torch.Tensor) -> bool:
-        return y.dtype == self.dtype and y.numel() * 2 <= self.capacity and (y.numel() * y.element_size()) % 16 == 0
+        nbytes = y.numel() * y.element_size()
+        return y.dtype == self.dtype and y.numel() * 2 <= self.capacity and nbytes % 16 == 0 and nbytes <= self.MAX_BYTES
 
     def __call__(self, y: torch.Tensor) -> torch.Tensor:
         from . import _lib

@@ -52,7 +52,7 @@ def test_fast_argmax_first_occurrence():
 
 
 def test_traffic_json_reproducible_from_launch_list(tmp_path):
-    csv = os.path.join(ROOT, "profiles", "r01k_launches.csv")
+    csv = os.path.join(ROOT, "profiles", "r03b_launches.csv")
     want = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     out = tmp_path / "t.json"
     subprocess.run([sys.executable, os.path.join(ROOT, "tools", "traffic_from_ncu.py"), csv, "128", str(out)], check=True,
