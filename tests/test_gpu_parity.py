@@ -300,6 +300,10 @@ def test_qmm_gemm_ts_vs_oracle(cuda_device, bits, gs):
     for (M, N, K) in ((5, 128, 1024), (16, 200, 1024), (17, 130, 2048), (33, 384, 1024), (100, 256, 2048), (200, 128, 1024),
                       (300, 130, 4096)):
         _run_case(g, cuda_device, "gemm_ts", bits, gs, M, N, K, seed=bits + gs + M, with_bias=(M == 100), tol=1e-2)
+    # shortest loops and thinnest tiles: one or two 256-k stages, fewer rows than a tile, a single row of x
+    if gs < 128:  # (K / 128) * 2 bytes would not be a legal TMA row pitch
+        for (M, N, K) in ((9, 3, 256), (1, 1, 512), (40, 129, 512)):
+            _run_case(g, cuda_device, "gemm_ts", bits, gs, M, N, K, seed=bits + gs + N, tol=1e-2)
 
 
 @pytest.mark.parametrize("M,N,K,bits,gs", [(8, 512, 4096, 4, 64), (32, 512, 4096, 4, 64), (64, 640, 6144, 4, 128), (17, 128, 8192, 2, 64),
