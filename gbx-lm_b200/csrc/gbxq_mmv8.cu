@@ -33,15 +33,15 @@ using namespace mmv8;
 namespace {
 
 // BITS, GS = group size, MT = tokens (1, 2, 4), CPW = chunk columns per warp, R = rows per warp and stage (4 or 8)
-template <int BITS, int GS, int MT, int CPW, int R>
+template <int BITS, int GS, int MT, int CPW, int R, bool PARTIAL>
 __global__ void __launch_bounds__(kThreads, kMinCtas) mmv8_kernel(const Mmv8Params p, const __grid_constant__ ArParams ar) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    mmv8_body<BITS, GS, MT, CPW, R>(p, (int)blockIdx.x, smem, nullptr, &ar);
+    mmv8_body<BITS, GS, MT, CPW, R, false, PARTIAL>(p, (int)blockIdx.x, smem, nullptr, &ar);
 }
 
-template <int BITS, int GS, int MT, int CPW, int R>
-int launch_inst(const Mmv8Params& p, const ArParams& ar, const Plan& pl, cudaStream_t st) {
-    auto kern = mmv8_kernel<BITS, GS, MT, CPW, R>;
+template <int BITS, int GS, int MT, int CPW, int R, bool PARTIAL>
+int launch_inst2(const Mmv8Params& p, const ArParams& ar, const Plan& pl, cudaStream_t st) {
+    auto kern = mmv8_kernel<BITS, GS, MT, CPW, R, PARTIAL>;
     static DeviceOnce configured;  // per device: the attribute is a per-device property
     if (configured.need()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCap);
@@ -61,6 +61,15 @@ int launch_inst(const Mmv8Params& p, const ArParams& ar, const Plan& pl, cudaStr
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p, ar);
     count_launch();
     return check_cuda(e);
+}
+
+template <int BITS, int GS, int MT, int CPW, int R>
+int launch_inst(const Mmv8Params& p, const ArParams& ar, const Plan& pl, cudaStream_t st) {
+    if constexpr (GS == 128 && MT <= 2) {  // the half-full-column instantiations (make_plan admits nothing else)
+        if (pl.partial) return launch_inst2<BITS, GS, MT, CPW, R, true>(p, ar, pl, st);
+    }
+    if (pl.partial) return GBXQ_EUNSUPPORTED;
+    return launch_inst2<BITS, GS, MT, CPW, R, false>(p, ar, pl, st);
 }
 
 template <int BITS, int GS, int MT>
@@ -119,7 +128,7 @@ bool mmv8_supported(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype
     if (((uintptr_t)x | (uintptr_t)w) & 15) return false;
     if ((uintptr_t)y & 1) return false;
     if ((K * 2) % 16) return false;
-    const Plan pl = make_plan(M, N, K, bits, gs);
+    const Plan pl = make_plan(M, N, K, bits, gs, 0, true, true);
     if (!pl.ok) return false;
     return pl.cpw * pl.mt <= 8;  // register budget of the stationary digit fragments
 }
@@ -133,7 +142,7 @@ int launch_mmv8(const void* x, const uint32_t* w, const void* s, const void* b, 
 int launch_mmv8_ar(const void* x, const uint32_t* w, const void* s, const void* b, const void* bias, void* y, int64_t M,
                    int64_t N, int64_t K, int bits, int gs, const gbxq_comm* comm, cudaStream_t st) {
     if (((uintptr_t)s | (uintptr_t)b) & 15) return GBXQ_EUNSUPPORTED;
-    const Plan pl = make_plan(M, N, K, bits, gs);
+    const Plan pl = make_plan(M, N, K, bits, gs, 0, true, true);
     if (!pl.ok || pl.cpw * pl.mt > 8) return GBXQ_EUNSUPPORTED;
     Mmv8Params p = make_params(pl, x, w, s, b, bias, y, M, N, K, bits, gs, mmv_get_pdl_mode() >= 2 ? 1 : 0);
     ArParams ar{};

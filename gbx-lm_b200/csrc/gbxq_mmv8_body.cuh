@@ -209,7 +209,9 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
 // STREAM = false: the whole CTA of a one-call launch (barrier set-up, producer warp, consumers, epilogue).
 // STREAM = true: one call of a persistent chain, entered by the kCW consumer warps only; barriers (empty barriers
 // initialised to kCW arrivals) and the producer live in the caller, `sc` carries the ring position.
-template <int BITS, int GS, int MT, int CPW, int R, bool STREAM = false>
+// PARTIAL: the row ends in the middle of a chunk column (G % 4 == 2; tensor-parallel K shards).  A separate instantiation:
+// compiled into the common kernels the three extra predicates cost the 8B step 1.7 % (r03i: 0.5221 -> 0.5134).
+template <int BITS, int GS, int MT, int CPW, int R, bool STREAM = false, bool PARTIAL = false>
 __device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, uint8_t* smem, StreamCtx* sc = nullptr,
                                           const ArParams* ar = nullptr) {
     const bool ar_on = !STREAM && ar != nullptr && ar->world > 1;
@@ -350,7 +352,8 @@ __device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, ui
 #pragma unroll
             for (int jj = 0; jj < JB; jj++) {
                 const int c = cwi + (j0 + jj) * p.cw;
-                const bool ld = (c < p.nch) && (m < p.M);
+                // groups past the end of the row (G % 4 == 2: the last chunk column holds two live slices) read zeros
+                const bool ld = (c < p.nch) && (!PARTIAL || c * S + bsl < p.G) && (m < p.M);
                 const int64_t k0 = ((int64_t)c * S + bsl) * GS + t * CQ;
                 const uint4* src = reinterpret_cast<const uint4*>(p.x + (size_t)m * p.K + k0);
 #pragma unroll
@@ -444,7 +447,7 @@ __device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, ui
             // tree of the R = 8 geometry bit for bit (single, grouped and chain launches must agree)
             const int idx = R == 16 ? bq + i * LPR : bq * NGL + i;
             const int c = cwi + (idx / S) * p.cw;
-            const bool on = idx < CPW * S && c < p.nch;
+            const bool on = idx < CPW * S && c < p.nch && (!PARTIAL || c * S + idx % S < p.G);
 #pragma unroll
             for (int m = 0; m < MT; m++) xg[i][m] = on ? myx[idx * MT + m] : 0.f;
             bofs[i] = (uint32_t)(p.tr + lrow0 + brow) * g2 + (on ? (uint32_t)(c * S + idx % S) * 2u : 0u);
@@ -456,6 +459,16 @@ __device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, ui
         // scale of the slice this lane's accumulators belong to (slice t of the chunk column), row = wrow
         const uint32_t sofT = (uint32_t)wrow * g2 + (uint32_t)(cwi * S + t) * 2u;
         const uint32_t sstride = (uint32_t)p.cw * S * 2u;
+        // Scale offset per chunk column.  Where this lane's slice t of column j lies past the row's last group (G % 4 == 2)
+        // its weight reads run into the next row -- exact zeros once multiplied with the zero activations of a dead slice,
+        // in the integer domain -- and the scale read is redirected to live slice t - 2 of the same column: always a real
+        // scale, never stale shared memory (a NaN there would survive the multiplication by zero).  No cost in the loop.
+        uint32_t sof[PARTIAL ? CPW : 1];
+        if constexpr (PARTIAL) {
+#pragma unroll
+            for (int j = 0; j < CPW; j++)
+                sof[j] = (uint32_t)j * sstride + sofT - (((cwi + j * p.cw) * S + t >= p.G && t >= 2) ? 4u : 0u);
+        }
 
         STAMP(2);
         for (int ra = 0; ra < rows; ra += spr) {
@@ -475,7 +488,7 @@ __device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, ui
                 uint32_t wa[NWORD], wb[NWORD];
                 load_chunk<BITS, CQ>(rbase + offA, wa);
                 load_chunk<BITS, CQ>(rbase + offB, wb);
-                const float sc = lds_bf16(sslot + (uint32_t)(lrow0 + q * W) * g2 + j * sstride + sofT);
+                const float sc = lds_bf16(sslot + (uint32_t)(lrow0 + q * W) * g2 + (PARTIAL ? sof[PARTIAL ? j : 0] : j * sstride + sofT));
                 const int kZero4[4] = {0, 0, 0, 0};
                 int T[MT][2];  // [token][part]: 256 * hi + lo of the meaningful part's group
 #pragma unroll
@@ -672,6 +685,7 @@ __device__ __forceinline__ void mmv8_body(const Mmv8Params& p, const int bid, ui
 struct Plan {
     bool ok;
     int mt, cpw, R, nch, cw, rg, tr, stages, grid, row_unit;
+    bool partial;  // G % 4 == 2: the last chunk column is half full (PARTIAL instantiation)
     uint32_t slot_bytes, sb_off;
     size_t smem;
 };
@@ -682,7 +696,8 @@ inline int env_int(const char* name, int dflt) {
 }
 
 // grid_want > 0: the number of CTAs this layer may use (a segment of a grouped launch); 0: the whole device
-inline Plan make_plan(int64_t M, int64_t N, int64_t K, int bits, int gs, int grid_want = 0, bool allow_r16 = true) {
+inline Plan make_plan(int64_t M, int64_t N, int64_t K, int bits, int gs, int grid_want = 0, bool allow_r16 = true,
+                      bool allow_partial = false) {
     Plan pl{};
     if (!(bits == 2 || bits == 3 || bits == 4 || bits == 6 || bits == 8) || M < 1 || M > 4 || N < 1) return pl;
     if ((bits == 2 || bits == 3 || bits == 6) && gs == 32) return pl;  // a thread chunk would be a fraction of a word
@@ -690,12 +705,16 @@ inline Plan make_plan(int64_t M, int64_t N, int64_t K, int bits, int gs, int gri
     // S | G.  The scales / biases of a stage travel as ONE bulk copy (the rows of a stage are contiguous), which needs a
     // 16-byte aligned start: any row when G % 8 == 0; with G % 8 == 4 (tensor-parallel K shards: Qwen2.5-32B down_proj
     // K/2 = 13824 at gs 128) every CTA range and stage must start on an even row -> rows are shared out in units of 4
-    if (G % 4) return pl;
+    // G % 4 == 2 (tensor-parallel K shards: Qwen2.5-32B at tp4, o_proj 1280 = 10 and down_proj 6912 = 54 groups of 128):
+    // the last chunk column is half full; its dead slices multiply zero activations
+    pl.partial = (G % 4) != 0;
+    // served by the one-call launches at group size 128 and <= 2 rows of x only (the instantiations that exist)
+    if (G % 2 || G < 2 || (pl.partial && !(allow_partial && gs == 128 && M <= 2))) return pl;
     pl.row_unit = (G % 8) ? 4 : 1;
     if (pl.row_unit == 4 && (N % 4)) return pl;
     const int64_t row_bytes = K * bits / 8;
     pl.mt = M == 1 ? 1 : (M == 2 ? 2 : 4);
-    pl.nch = (int)(G / S);
+    pl.nch = (int)((G + S - 1) / S);
     static const int force_cpw = env_int("GBXQ_MMV8_CPW", 0);
     static const int grid_mult = env_int("GBXQ_MMV8_GRID_MULT", 2 / kWide);
     static const int stage_kb = env_int("GBXQ_MMV8_STAGE_KB", 32 * kWide);

@@ -141,6 +141,32 @@ def test_qmm_mmv8_rows_of_scales_only_8_byte_aligned(cuda_device, bits, gs, K):
         _run_case(g, cuda_device, "mmv8", bits, gs, 1, 70, K, seed=1)
 
 
+@pytest.mark.parametrize("bits,gs,K", [(4, 128, 1280), (4, 128, 6912), (2, 128, 768), (8, 128, 256 + 512), (3, 128, 1792), (6, 128, 768)])
+def test_qmm_mmv8_half_full_last_chunk_column(cuda_device, bits, gs, K):
+    """K / group_size = 2 (mod 4): the row ends in the middle of a 4-group chunk column (Qwen2.5-32B at tp4: o_proj K/4 =
+    1280 and down_proj K/4 = 6912 at gs 128).  Served by the one-call decode launches at group size 128 and <= 2 rows of
+    x (a separate instantiation): the dead slices multiply zero activations and their scale reads, which would run into
+    the next row or into stale shared memory behind the last row of a stage, are redirected to a live slice."""
+    g = _ops()
+    from gbx_lm_b200 import _lib
+
+    assert (K // gs) % 4 == 2
+    for M in (1, 2):
+        for N in (72, 1028, 4):
+            _run_case(g, cuda_device, "mmv8", bits, gs, M, N, K, seed=bits + gs + M + N, with_bias=(M == 2))
+    assert _lib.get().gbxq_select_kernel(1, 1024, K, bits, gs, 0) == _lib.KERNEL_MMV8
+    with pytest.raises(RuntimeError):  # 4 rows of x: no such instantiation; auto dispatch serves the call elsewhere
+        _run_case(g, cuda_device, "mmv8", bits, gs, 4, 72, K, seed=1)
+    _run_case(g, cuda_device, "auto", bits, gs, 4, 72, K, seed=1, tol=1e-2)
+    # a grouped call on such a K falls back to one launch per segment: same results
+    segs = []
+    for i, N in enumerate((256, 64)):
+        segs.append(_Seg(layer_to_cuda(A.synth_layer(N, K, bits, gs, seed=90 + i), cuda_device), bits, gs))
+    x = bf16_from_bits(A.synth_x(1, K, seed=3), cuda_device)
+    for sg, y in zip(segs, g.quantized_matmul_grouped(x, segs)):
+        assert torch.equal(y, g.quantized_matmul(x, sg.qweight, sg.scales, sg.zeros, True, gs, bits))
+
+
 def test_qmm_mmv8_block_fixed_point_ranges(cuda_device):
     """The integer kernel represents x per (token, group) as 15-bit block fixed point: check wide dynamic range inside a
     group (outlier channels), tiny and huge magnitudes, exact zeros, and that inf / nan poison only what they should."""
@@ -300,9 +326,9 @@ def test_qmm_gemm_ts_vs_oracle(cuda_device, bits, gs):
     for (M, N, K) in ((5, 128, 1024), (16, 200, 1024), (17, 130, 2048), (33, 384, 1024), (100, 256, 2048), (200, 128, 1024),
                       (300, 130, 4096)):
         _run_case(g, cuda_device, "gemm_ts", bits, gs, M, N, K, seed=bits + gs + M, with_bias=(M == 100), tol=1e-2)
-    # shortest loops and thinnest tiles: one or two 256-k stages, fewer rows than a tile, a single row of x
-    if gs < 128:  # (K / 128) * 2 bytes would not be a legal TMA row pitch
-        for (M, N, K) in ((9, 3, 256), (1, 1, 512), (40, 129, 512)):
+    # shortest loops and thinnest tiles: one or two 256-k stages, fewer rows than a tile, a few rows of x
+    for (M, N, K) in ((9, 16, 256), (3, 24, 512), (40, 129, 512)):
+        if (K // gs) % 8 == 0:  # a row of scales must be a legal TMA row pitch (16 bytes)
             _run_case(g, cuda_device, "gemm_ts", bits, gs, M, N, K, seed=bits + gs + N, tol=1e-2)
 
 
