@@ -20,6 +20,13 @@
 //   * split-K over blockIdx.z for skinny batches exactly as in gbxq_gemm_sm100.cu (deterministic reduction order).
 #include <cstdlib>
 
+//
+// This file is compiled twice.  gbxq_gemm_ts_direct_sm100.cu includes it with GBXQ_TS_DIRECT defined: the variant for
+// matrices whose row of scales is not a legal TMA row pitch (K / group_size not a multiple of 8: tensor-parallel K
+// shards such as Qwen2.5-32B o_proj K/4 = 1280 = 10 groups of 128), where the dequant threads read their (row, group)
+// scale and bias from global memory one stage ahead instead of from the TMA-fed scale ring.  Preprocessor blocks, not a
+// template flag or a run-time branch: either of those changed the register allocation of the common kernel and cost
+// prefill 3-5 % in same-box A/B runs (r03l-r03n).
 #include "gbxq_umma.cuh"
 
 namespace gbxq {
@@ -27,6 +34,16 @@ namespace gbxq {
 void gemm_split_plan(int64_t M, int64_t N, int64_t K, int* splits, int* kb_per_split, size_t* ws_bytes);
 bool encode_tensor_map_2d_sw(void* tm, int dtype, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
                              uint32_t box_inner, uint32_t box_outer, int swizzle_bytes);
+
+#ifdef GBXQ_TS_DIRECT
+#define TS_KERNEL gemm_ts_direct_kernel
+#define TS_LAUNCH launch_gemm_ts_direct
+#else
+#define TS_KERNEL gemm_ts_kernel
+#define TS_LAUNCH launch_gemm_ts
+int launch_gemm_ts_direct(const void* x, const uint32_t* w, const void* s, const void* b, const void* bias, void* y, int64_t M,
+                          int64_t N, int64_t K, int bits, int gs, void* workspace, size_t workspace_bytes, cudaStream_t st);
+#endif
 
 namespace {
 
@@ -59,6 +76,11 @@ struct TsParams {
     const uint8_t* w_raw;      // packed weights (for the L2 prefetch of the CTA's rows)
     int64_t row_bytes;
     int rotate;                // 1: CTAs start their k loop at different stages (see stage_of)
+#ifdef GBXQ_TS_DIRECT
+    const uint16_t* s_raw;     // scales / biases [N, G] read directly by the dequant threads
+    const uint16_t* b_raw;
+    int64_t G;
+#endif
     unsigned long long* dbg;   // development aid (gbxq_debug_ts_timeline): CTA 0 stamps %globaltimer, see tools/ts_timeline.py
 };
 
@@ -144,7 +166,7 @@ __device__ __forceinline__ uint32_t pick16(const uint4& v, int g) {
 
 template <int BITS, int BN>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_ts_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+TS_KERNEL(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                const __grid_constant__ CUtensorMap tmap_s, const __grid_constant__ CUtensorMap tmap_b, const TsParams p) {
     using C = Cfg<BITS, BN>;
     constexpr int XS = C::XS, WS = C::WS, SS = C::SS, AS = kAStages;
@@ -251,6 +273,7 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         if (!p.early_w) griddep_wait();
         const uint32_t wring_b = smem_u32(wring), sring_b = smem_u32(sring);
         for (int s = 0; s < nst; s++) {
+#ifndef GBXQ_TS_DIRECT
             if ((s & (st_per_s - 1)) == 0) {
                 const int sl = s >> sps_shift, ss = sl % SS;
                 mbar_wait(&sempty[ss], ((uint32_t)(sl / SS) & 1u) ^ 1u);
@@ -262,6 +285,7 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 }
                 __syncwarp();
             }
+#endif
             const int ws = s % WS;
             mbar_wait(&wempty[ws], ((uint32_t)(s / WS) & 1u) ^ 1u);
             if (elect_one()) {
@@ -328,16 +352,36 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         uint32_t f_wbar = smem_u32(wfull), f_sbar = smem_u32(sfull);
         uint32_t f_wph = 0, f_sph = 0;
         int f_ws = 0, f_ss = 0, f_sin = 0;
+#ifdef GBXQ_TS_DIRECT
+        int f_idx = 0;
+        uint32_t d_s[kH], d_b[kH];                           // the stage's raw scale / bias per half
+        const bool d_row = (int64_t)n0 + r < p.N;
+        const int64_t d_off = ((int64_t)n0 + r) * p.G;
+#endif
         auto fetch = [&]() {
+#ifdef GBXQ_TS_DIRECT
+            {
+                const int k0 = (st_lo + stage_of(f_idx)) * kStageK + kq * 32;
+#pragma unroll
+                for (int h = 0; h < kH; h++) {
+                    const int64_t at = d_off + ((k0 + h * kHalfK) >> p.gs_shift);
+                    d_s[h] = d_row ? (uint32_t)__ldg(p.s_raw + at) : 0u;
+                    d_b[h] = d_row ? (uint32_t)__ldg(p.b_raw + at) : 0u;
+                }
+                f_idx++;
+            }
+#endif
             mbar_wait_u32(f_wbar + 8u * f_ws, f_wph);
 #pragma unroll
             for (int h = 0; h < kH; h++) load_codes<BITS>(f_w + (uint32_t)f_ws * C::W_SLOT + (uint32_t)h * C::W_HALF, r, kq, w[h]);
+#ifndef GBXQ_TS_DIRECT
             if (f_sin == 0) {
                 mbar_wait_u32(f_sbar + 8u * f_ss, f_sph);
                 sreg = lds128(f_s + (uint32_t)f_ss * C::S_SLOT);
                 breg = lds128(f_s + (uint32_t)f_ss * C::S_SLOT + kTileN * 16u);
                 if (++f_ss == SS) { f_ss = 0; f_sph ^= 1u; }
             }
+#endif
             f_sin = (f_sin + 1) & sps_mask;
             if (++f_ws == WS) { f_ws = 0; f_wph ^= 1u; }
         };
@@ -350,7 +394,12 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 #pragma unroll
             for (int h = 0; h < kH; h++) {
                 const int gl = (c_sin << gl_shift) + gl_base[h];  // group inside the 8-group slot
+#ifdef GBXQ_TS_DIRECT
+                const uint32_t sraw = d_s[h], braw = d_b[h];
+                (void)gl;
+#else
                 const uint32_t sraw = pick16(sreg, gl), braw = pick16(breg, gl);
+#endif
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
                     uint32_t o[4];
@@ -371,7 +420,9 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive_u32(we_bar + 8u * c_ws);         // the packed words of stage s were consumed above
+#ifndef GBXQ_TS_DIRECT
                 if (c_sin == sps_mask || s == nst - 1) mbar_arrive_u32(se_bar + 8u * c_ss);  // ... and the slot's scales
+#endif
             }
             if (c_sin == sps_mask) { if (++c_ss == SS) c_ss = 0; }
             c_sin = (c_sin + 1) & sps_mask;
@@ -468,7 +519,7 @@ template <int BITS, int BN>
 int launch_inst(const Maps& mp, const TsParams& p, cudaStream_t st) {
     constexpr size_t smem = Cfg<BITS, BN>::SMEM;
     static_assert(smem <= 227 * 1024, "shared memory budget");
-    auto kern = gemm_ts_kernel<BITS, BN>;
+    auto kern = TS_KERNEL<BITS, BN>;
     static DeviceOnce configured;
     if (configured.need()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -507,6 +558,7 @@ int pick_bn(int64_t M) { return M <= 16 ? 16 : (M <= 32 ? 32 : (M <= 64 ? 64 : (
 
 }  // namespace
 
+#ifndef GBXQ_TS_DIRECT
 void gemm_ts_debug_timeline(unsigned long long* buf) { g_ts_dbg = buf; }
 
 bool gemm_ts_supported(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype, const void* x, const void* w,
@@ -514,17 +566,22 @@ bool gemm_ts_supported(int64_t M, int64_t N, int64_t K, int bits, int gs, int dt
     if (dtype != GBXQ_BF16 || M < 1 || N < 1) return false;
     if (K % kStageK) return false;              // whole 256-k stages
     if ((K * bits / 8) % 16) return false;      // TMA: packed row pitch must be a multiple of 16 bytes
-    if (((K / gs) * 2) % 16) return false;      // TMA: scale row pitch must be a multiple of 16 bytes
     if (((uintptr_t)x | (uintptr_t)w) & 15) return false;
     if ((uintptr_t)y & 1) return false;
     if (M > (int64_t)1 << 24 || (N + kTileN - 1) / kTileN > 65535 * 32) return false;
     return tma_encode_available();
 }
 
-int launch_gemm_ts(const void* x, const uint32_t* w, const void* s, const void* b, const void* bias, void* y, int64_t M,
-                   int64_t N, int64_t K, int bits, int gs, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+#endif
+
+int TS_LAUNCH(const void* x, const uint32_t* w, const void* s, const void* b, const void* bias, void* y, int64_t M, int64_t N,
+              int64_t K, int bits, int gs, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     if (!tma_encode_available()) return GBXQ_EUNSUPPORTED;
-    if (((uintptr_t)s | (uintptr_t)b) & 15) return GBXQ_EUNSUPPORTED;
+#ifndef GBXQ_TS_DIRECT
+    // a row of scales that is no legal TMA row pitch (or unaligned scale tensors): the direct-scale variant
+    if (((((uintptr_t)s | (uintptr_t)b) & 15) != 0) || (((K / gs) * 2) % 16 != 0))
+        return launch_gemm_ts_direct(x, w, s, b, bias, y, M, N, K, bits, gs, workspace, workspace_bytes, st);
+#endif
     const int bn = pick_bn(M);
     if ((M + bn - 1) / bn > 65535) return GBXQ_EUNSUPPORTED;
     Maps mp;
@@ -532,8 +589,14 @@ int launch_gemm_ts(const void* x, const uint32_t* w, const void* s, const void* 
     const int swz = bits == 4 ? 64 : (bits == 2 ? 32 : (bits == 8 ? 128 : 0));
     bool ok = encode_tensor_map_2d_sw(&mp.x, 0, x, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, kAtomK, (uint32_t)bn, 128);
     ok = ok && encode_tensor_map_2d_sw(&mp.w, 1, w, words, (uint64_t)N, words * 4, (uint32_t)(4 * bits), kTileN, swz);
+#ifdef GBXQ_TS_DIRECT
+    mp.s = mp.w;  // never used
+    mp.b = mp.w;
+    (void)G;
+#else
     ok = ok && encode_tensor_map_2d_sw(&mp.s, 0, s, G, (uint64_t)N, G * 2, 8, kTileN, 0);
     ok = ok && encode_tensor_map_2d_sw(&mp.b, 0, b, G, (uint64_t)N, G * 2, 8, kTileN, 0);
+#endif
     if (!ok) return GBXQ_EUNSUPPORTED;
     TsParams p{};
     p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
@@ -551,6 +614,11 @@ int launch_gemm_ts(const void* x, const uint32_t* w, const void* s, const void* 
         return e ? atoi(e) : 0;
     }();
     p.rotate = rotate;
+#ifdef GBXQ_TS_DIRECT
+    p.s_raw = reinterpret_cast<const uint16_t*>(s);
+    p.b_raw = reinterpret_cast<const uint16_t*>(b);
+    p.G = (int64_t)(K / gs);
+#endif
     p.dbg = g_ts_dbg;
     g_ts_dbg = nullptr;  // one launch
     {

@@ -327,9 +327,10 @@ def test_qmm_gemm_ts_vs_oracle(cuda_device, bits, gs):
                       (300, 130, 4096)):
         _run_case(g, cuda_device, "gemm_ts", bits, gs, M, N, K, seed=bits + gs + M, with_bias=(M == 100), tol=1e-2)
     # shortest loops and thinnest tiles: one or two 256-k stages, fewer rows than a tile, a few rows of x
-    for (M, N, K) in ((9, 16, 256), (3, 24, 512), (40, 129, 512)):
-        if (K // gs) % 8 == 0:  # a row of scales must be a legal TMA row pitch (16 bytes)
-            _run_case(g, cuda_device, "gemm_ts", bits, gs, M, N, K, seed=bits + gs + N, tol=1e-2)
+    # (where K / group_size is not a multiple of 8 a row of scales is no legal TMA row pitch: the dequant threads then
+    # read their scales from global memory -- tensor-parallel K shards: 1280 = 10 and 6912 = 54 groups of 128)
+    for (M, N, K) in ((9, 16, 256), (3, 24, 512), (40, 129, 512), (33, 200, 1280), (300, 136, 6912), (12, 512, 768)):
+        _run_case(g, cuda_device, "gemm_ts", bits, gs, M, N, K, seed=bits + gs + N, with_bias=(M == 33), tol=1e-2)
 
 
 @pytest.mark.parametrize("M,N,K,bits,gs", [(8, 512, 4096, 4, 64), (32, 512, 4096, 4, 64), (64, 640, 6144, 4, 128), (17, 128, 8192, 2, 64),
