@@ -197,6 +197,7 @@ TS_KERNEL(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CU
     const int sps_shift = p.gs_shift - 5;                                             // log2(stages per 8-group scale slot)
     const int st_per_s = 1 << sps_shift;                                              // 1, 2, 4 for group sizes 32, 64, 128
     const int sl_lo = st_lo >> sps_shift;
+    (void)sl_lo;
     // Optional k rotation (GBXQ_TS_ROTATE=1): CTA b walks its stages starting at stage rot(b) and wraps around, so that
     // the CTAs of a grid do not all ask L2 for the same x tile at the same time.  Measured (r02v-r02y): no gain at small
     // batches (the loop is bound by the dequant warps' instruction issue, not by x) and -5 % on prefill tiles, where
@@ -336,6 +337,7 @@ TS_KERNEL(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CU
         const uint32_t wring_u32 = smem_u32(wring), sring_u32 = smem_u32(sring);
         const uint32_t a_lane = tmem_base + kTmemAOff + ((uint32_t)(rq * 32) << 16) + (uint32_t)(kq * 16);
         uint4 sreg = make_uint4(0u, 0u, 0u, 0u), breg = sreg;
+        (void)sreg; (void)breg;
         // Software pipeline over the stages: the tcgen05.st of stage s is only waited for (and the stage handed to the
         // MMA warp) after the ALU work of stage s+1, and the packed words of stage s+1 are fetched from shared memory
         // while the store of stage s is in flight -- a warp's per-stage latency chain is its ~80 ALU instructions, not
@@ -352,6 +354,7 @@ TS_KERNEL(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CU
         uint32_t f_wbar = smem_u32(wfull), f_sbar = smem_u32(sfull);
         uint32_t f_wph = 0, f_sph = 0;
         int f_ws = 0, f_ss = 0, f_sin = 0;
+        (void)f_s; (void)f_sbar; (void)f_sph; (void)f_ss;
 #ifdef GBXQ_TS_DIRECT
         int f_idx = 0;
         uint32_t d_s[kH], d_b[kH];                           // the stage's raw scale / bias per half
