@@ -18,7 +18,7 @@ constexpr int kWide = kCW / 8;                // shared memory, stage and ring b
 constexpr int kSmemCap = 110 * 1024 * kWide;
 constexpr int kThreads = (kCW + 1) * 32;      // + producer warp
 constexpr int kMaxStages = 8;                // barrier slots; one-call launches plan at most kPlanStages
-constexpr int kPlanStages = 4;
+constexpr int kPlanStages = GBXQ_MMV8_CW == 16 ? 3 : 4;  // r03s/r03t: three (larger-share) stages 0.526 vs 0.522 on the 8B step
 constexpr int kArMaxCtas = GBXQ_RP_MAX_CTAS;
 #ifndef GBXQ_MMV8_MINCTAS
 #define GBXQ_MMV8_MINCTAS (GBXQ_MMV8_CW == 8 ? 2 : 1)
