@@ -23,6 +23,8 @@ EXPORTS = (
     "gbxq_qmm",
     "gbxq_qmm_ex",
     "gbxq_qmm_grouped",
+    "gbxq_qmm_grouped_ws",
+    "gbxq_grouped_workspace_bytes",
     "gbxq_stream_plan",
     "gbxq_qmm_stream",
     "gbxq_workspace_bytes",
@@ -119,6 +121,10 @@ def get() -> ctypes.CDLL:
     lib.gbxq_qmm_ex.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, ci, ci, ci, ci, vp, sz, vp]
     lib.gbxq_qmm_grouped.restype = ci
     lib.gbxq_qmm_grouped.argtypes = [ctypes.POINTER(Segment), ci, vp, i64, i64, ci, vp]
+    lib.gbxq_qmm_grouped_ws.restype = ci
+    lib.gbxq_qmm_grouped_ws.argtypes = [ctypes.POINTER(Segment), ci, vp, i64, i64, ci, vp, sz, vp]
+    lib.gbxq_grouped_workspace_bytes.restype = sz
+    lib.gbxq_grouped_workspace_bytes.argtypes = [ctypes.POINTER(Segment), ci, i64, i64, ci]
     lib.gbxq_stream_plan.restype = ci
     lib.gbxq_stream_plan.argtypes = [ctypes.POINTER(StreamCall), ci, i64, ci, vp, sz, ctypes.POINTER(StreamInfo)]
     lib.gbxq_qmm_stream.restype = ci

@@ -32,6 +32,7 @@ SOURCES = [
     "gbxq_gemm_sm100.cu",
     "gbxq_gemm_ts_sm100.cu",
     "gbxq_gemm_ts_direct_sm100.cu",
+    "gbxq_gemm_ts_grouped_sm100.cu",
     "gbxq_allreduce.cu",
 ]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

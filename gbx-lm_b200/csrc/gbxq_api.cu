@@ -199,6 +199,25 @@ int gbxq_qmm_rowpar_allreduce(const void* x, const uint32_t* qweight, const void
 }
 
 int gbxq_qmm_grouped(const gbxq_segment* segs, int nseg, const void* x, int64_t M, int64_t K, int dtype, void* stream) {
+    return gbxq_qmm_grouped_ws(segs, nseg, x, M, K, dtype, nullptr, 0, stream);
+}
+
+size_t gbxq_grouped_workspace_bytes(const gbxq_segment* segs, int nseg, int64_t M, int64_t K, int dtype) {
+    if (!segs || nseg < 1 || dtype != GBXQ_BF16 || M <= 4) return 0;
+    size_t need = 0;
+    for (int i = 0; i < nseg; i++) {  // the per-segment fallback uses the same scratch, one call after the other
+        const size_t b = gbxq_workspace_bytes(M, segs[i].N, K, segs[i].bits, segs[i].group_size, dtype);
+        if (b > need) need = b;
+    }
+    if (nseg >= 2 && nseg <= 3) {
+        const size_t b = gemm_workspace_bytes(M, gemm_ts_grouped_npad(segs, nseg), K);
+        if (b > need) need = b;
+    }
+    return need;
+}
+
+int gbxq_qmm_grouped_ws(const gbxq_segment* segs, int nseg, const void* x, int64_t M, int64_t K, int dtype, void* workspace,
+                        size_t workspace_bytes, void* stream) {
     if (nseg < 0) return GBXQ_ESHAPE;
     if (nseg == 0) return GBXQ_OK;
     if (!segs) return GBXQ_ENULL;
@@ -218,10 +237,15 @@ int gbxq_qmm_grouped(const gbxq_segment* segs, int nseg, const void* x, int64_t 
         const int rc = launch_mmv8_grouped(segs, nseg, x, M, K, (cudaStream_t)stream);
         if (rc != GBXQ_EUNSUPPORTED) return rc;
     }
+    // decode batches / prefill: segments of one bit width and group size share ONE launch of the TMEM-operand GEMM
+    if (dtype == GBXQ_BF16 && nseg >= 2 && nseg <= 3 && ts_min_m() > 0 && M >= ts_min_m()) {
+        const int rc = launch_gemm_ts_grouped(segs, nseg, x, M, K, workspace, workspace_bytes, (cudaStream_t)stream);
+        if (rc != GBXQ_EUNSUPPORTED) return rc;
+    }
     for (int i = 0; i < nseg; i++) {
         const gbxq_segment& s = segs[i];
         const int rc = gbxq_qmm_ex(x, s.qweight, s.scales, s.biases, s.bias, s.y, M, s.N, K, s.bits, s.group_size, dtype,
-                                   GBXQ_KERNEL_AUTO, nullptr, 0, stream);
+                                   GBXQ_KERNEL_AUTO, workspace, workspace_bytes, stream);
         if (rc != GBXQ_OK) return rc;
     }
     return GBXQ_OK;

@@ -232,6 +232,9 @@ int launch_gemm(const void* x, const uint32_t* w, const void* s, const void* b, 
                 int64_t N, int64_t K, int bits, int gs, void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t gemm_workspace_bytes(int64_t M, int64_t N, int64_t K);
 void gemm_ts_debug_timeline(unsigned long long* buf);
+int64_t gemm_ts_grouped_npad(const gbxq_segment* segs, int nseg);
+int launch_gemm_ts_grouped(const gbxq_segment* segs, int nseg, const void* x, int64_t M, int64_t K, void* workspace,
+                           size_t workspace_bytes, cudaStream_t st);
 bool gemm_ts_supported(int64_t M, int64_t N, int64_t K, int bits, int gs, int dtype, const void* x, const void* w,
                        const void* y);
 int launch_gemm_ts(const void* x, const uint32_t* w, const void* s, const void* b, const void* bias, void* y, int64_t M,

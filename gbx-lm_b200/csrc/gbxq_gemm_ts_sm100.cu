@@ -45,6 +45,37 @@ int launch_gemm_ts_direct(const void* x, const uint32_t* w, const void* s, const
                           int64_t N, int64_t K, int bits, int gs, void* workspace, size_t workspace_bytes, cudaStream_t st);
 #endif
 
+// A third compilation (gbxq_gemm_ts_grouped_sm100.cu, GBXQ_TS_GROUPED): up to three projections that read the same x
+// (q|k|v, gate|up) and share bit width and group size as ONE launch -- the tiles of all segments in one grid, one
+// tensor-map triple per segment.  The macros below keep the tokens of the plain compilation unchanged.
+#ifdef GBXQ_TS_GROUPED
+#undef TS_KERNEL
+#define TS_KERNEL gemm_ts_grouped_kernel
+#define TS_SIG const __grid_constant__ TsMaps maps, const TsParams p
+#define TMAP_X &maps.x
+#define TMAP_W &maps.w[seg]
+#define TMAP_S &maps.s[seg]
+#define TMAP_B &maps.b[seg]
+#define P_N segN
+#define P_BIAS seg_bias
+#define P_Y seg_y
+#define P_WS seg_ws
+#define TILE_X ((int)blockIdx.x - tile_lo)
+#else
+#define TS_SIG                                                                                           \
+    const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,              \
+        const __grid_constant__ CUtensorMap tmap_s, const __grid_constant__ CUtensorMap tmap_b, const TsParams p
+#define TMAP_X &tmap_x
+#define TMAP_W &tmap_w
+#define TMAP_S &tmap_s
+#define TMAP_B &tmap_b
+#define P_N p.N
+#define P_BIAS p.bias
+#define P_Y p.y
+#define P_WS p.ws
+#define TILE_X blockIdx.x
+#endif
+
 namespace {
 
 using namespace umma;
@@ -64,6 +95,13 @@ constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTmemAOff = 256;
 constexpr size_t kCntBytes = 16384;  // counter header of the split-K workspace (as gbxq_gemm_sm100.cu)
 
+#ifdef GBXQ_TS_GROUPED
+struct TsMaps {  // one x map, one (packed codes, scales, biases) triple per segment
+    CUtensorMap x;
+    CUtensorMap w[3], s[3], b[3];
+};
+#endif
+
 struct TsParams {
     const __nv_bfloat16* bias;
     __nv_bfloat16* y;
@@ -76,6 +114,14 @@ struct TsParams {
     const uint8_t* w_raw;      // packed weights (for the L2 prefetch of the CTA's rows)
     int64_t row_bytes;
     int rotate;                // 1: CTAs start their k loop at different stages (see stage_of)
+#ifdef GBXQ_TS_GROUPED
+    int nseg;                  // segments of the launch: segment i owns grid tiles [tile0[i], tile0[i + 1])
+    int tile0[4];
+    int64_t seg_n[3];
+    const __nv_bfloat16* seg_bias[3];
+    __nv_bfloat16* seg_y[3];
+    int64_t seg_ws_off[3];     // floats: where the segment's split-K partials start in the workspace
+#endif
 #ifdef GBXQ_TS_DIRECT
     const uint16_t* s_raw;     // scales / biases [N, G] read directly by the dequant threads
     const uint16_t* b_raw;
@@ -166,8 +212,7 @@ __device__ __forceinline__ uint32_t pick16(const uint4& v, int g) {
 
 template <int BITS, int BN>
 __global__ void __launch_bounds__(kThreads, 1)
-TS_KERNEL(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-               const __grid_constant__ CUtensorMap tmap_s, const __grid_constant__ CUtensorMap tmap_b, const TsParams p) {
+TS_KERNEL(TS_SIG) {
     using C = Cfg<BITS, BN>;
     constexpr int XS = C::XS, WS = C::WS, SS = C::SS, AS = kAStages;
 
@@ -189,7 +234,18 @@ TS_KERNEL(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CU
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * kTileN;
+#ifdef GBXQ_TS_GROUPED
+    int seg = 0;
+#pragma unroll
+    for (int i = 1; i < 3; i++)
+        if (i < p.nseg && (int)blockIdx.x >= p.tile0[i]) seg = i;
+    const int tile_lo = p.tile0[seg];
+    const int64_t segN = p.seg_n[seg];
+    const __nv_bfloat16* seg_bias = p.seg_bias[seg];
+    __nv_bfloat16* seg_y = p.seg_y[seg];
+    float* seg_ws = p.ws + p.seg_ws_off[seg];
+#endif
+    const int n0 = TILE_X * kTileN;
     const int m0 = blockIdx.y * BN;
     const int st_all = (int)(p.K / kStageK);
     const int st_lo = p.splits > 1 ? (int)blockIdx.z * (p.kb_per_split >> 2) : 0;    // first stage of this split
@@ -236,10 +292,10 @@ TS_KERNEL(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CU
     }
     if (warp == 0) {
         if (lane == 0) {
-            tma_prefetch_desc(&tmap_x);
-            tma_prefetch_desc(&tmap_w);
-            tma_prefetch_desc(&tmap_s);
-            tma_prefetch_desc(&tmap_b);
+            tma_prefetch_desc(TMAP_X);
+            tma_prefetch_desc(TMAP_W);
+            tma_prefetch_desc(TMAP_S);
+            tma_prefetch_desc(TMAP_B);
         }
         __syncwarp();
         tmem_alloc(tmem_slot, kTmemCols);
@@ -264,7 +320,7 @@ TS_KERNEL(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CU
             mbar_wait(&empty_b[s], ((uint32_t)(a / XS) & 1u) ^ 1u);
             if (elect_one()) {
                 mbar_arrive_expect_tx(&full_b[s], C::B_BYTES);
-                tma_load_2d_u32(xring_u32 + (uint32_t)s * C::B_BYTES, &tmap_x, (kAtomsPerStage * (st_lo + stage_of(a / kAtomsPerStage)) + (a % kAtomsPerStage)) * kAtomK, m0,
+                tma_load_2d_u32(xring_u32 + (uint32_t)s * C::B_BYTES, TMAP_X, (kAtomsPerStage * (st_lo + stage_of(a / kAtomsPerStage)) + (a % kAtomsPerStage)) * kAtomK, m0,
                                 smem_u32(&full_b[s]));
             }
             __syncwarp();
@@ -281,8 +337,8 @@ TS_KERNEL(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CU
                 if (elect_one()) {
                     const int gsl = sl_lo + (stage_of(s) >> sps_shift);  // the slot's place in the matrix
                     mbar_arrive_expect_tx(&sfull[ss], C::S_SLOT);
-                    tma_load_2d_u32(sring_b + (uint32_t)ss * C::S_SLOT, &tmap_s, gsl * 8, n0, smem_u32(&sfull[ss]));
-                    tma_load_2d_u32(sring_b + (uint32_t)ss * C::S_SLOT + kTileN * 16, &tmap_b, gsl * 8, n0, smem_u32(&sfull[ss]));
+                    tma_load_2d_u32(sring_b + (uint32_t)ss * C::S_SLOT, TMAP_S, gsl * 8, n0, smem_u32(&sfull[ss]));
+                    tma_load_2d_u32(sring_b + (uint32_t)ss * C::S_SLOT + kTileN * 16, TMAP_B, gsl * 8, n0, smem_u32(&sfull[ss]));
                 }
                 __syncwarp();
             }
@@ -293,7 +349,7 @@ TS_KERNEL(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CU
                 mbar_arrive_expect_tx(&wfull[ws], C::W_SLOT);
 #pragma unroll
                 for (int h = 0; h < kH; h++)
-                    tma_load_2d_u32(wring_b + (uint32_t)ws * C::W_SLOT + (uint32_t)h * C::W_HALF, &tmap_w,
+                    tma_load_2d_u32(wring_b + (uint32_t)ws * C::W_SLOT + (uint32_t)h * C::W_HALF, TMAP_W,
                                     ((st_lo + stage_of(s)) * kH + h) * 4 * BITS, n0, smem_u32(&wfull[ws]));
             }
             __syncwarp();
@@ -358,7 +414,7 @@ TS_KERNEL(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CU
 #ifdef GBXQ_TS_DIRECT
         int f_idx = 0;
         uint32_t d_s[kH], d_b[kH];                           // the stage's raw scale / bias per half
-        const bool d_row = (int64_t)n0 + r < p.N;
+        const bool d_row = (int64_t)n0 + r < P_N;
         const int64_t d_off = ((int64_t)n0 + r) * p.G;
 #endif
         auto fetch = [&]() {
@@ -447,8 +503,8 @@ TS_KERNEL(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CU
         griddep_wait();  // y may still be read by an earlier kernel of the stream
         const int er = rq * 32 + lane;
         const int64_t n = (int64_t)n0 + er;
-        const bool row_ok = n < p.N;
-        const float bias_f = (p.bias != nullptr && row_ok) ? __bfloat162float(p.bias[n]) : 0.f;
+        const bool row_ok = n < P_N;
+        const float bias_f = (P_BIAS != nullptr && row_ok) ? __bfloat162float(P_BIAS[n]) : 0.f;
         constexpr int QCOLS = BN / 4;
         constexpr int STEP = QCOLS >= 32 ? 32 : (QCOLS >= 16 ? 16 : (QCOLS >= 8 ? 8 : 4));
         const int cq = dw >> 2;
@@ -469,11 +525,11 @@ TS_KERNEL(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CU
                     const int64_t m = (int64_t)m0 + c0 + j;
                     if (m < p.M) {
                         if (p.splits > 1) {
-                            p.ws[((size_t)blockIdx.z * p.M + m) * p.N + n] = __uint_as_float(v[j]);
+                            P_WS[((size_t)blockIdx.z * p.M + m) * P_N + n] = __uint_as_float(v[j]);
                         } else {
                             float f = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[j])));
-                            if (p.bias != nullptr) f = __fadd_rn(f, bias_f);
-                            p.y[(size_t)m * p.N + n] = __float2bfloat16_rn(f);
+                            if (P_BIAS != nullptr) f = __fadd_rn(f, bias_f);
+                            P_Y[(size_t)m * P_N + n] = __float2bfloat16_rn(f);
                         }
                     }
                 }
@@ -495,10 +551,10 @@ TS_KERNEL(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CU
                         const int64_t m = (int64_t)m0 + c;
                         if (m < p.M) {
                             float acc = 0.f;
-                            for (int z = 0; z < p.splits; z++) acc += __ldcg(p.ws + ((size_t)z * p.M + m) * p.N + n);
+                            for (int z = 0; z < p.splits; z++) acc += __ldcg(P_WS + ((size_t)z * p.M + m) * P_N + n);
                             float f = __bfloat162float(__float2bfloat16_rn(acc));
-                            if (p.bias != nullptr) f = __fadd_rn(f, bias_f);
-                            p.y[(size_t)m * p.N + n] = __float2bfloat16_rn(f);
+                            if (P_BIAS != nullptr) f = __fadd_rn(f, bias_f);
+                            P_Y[(size_t)m * P_N + n] = __float2bfloat16_rn(f);
                         }
                     }
                 }
@@ -514,6 +570,7 @@ TS_KERNEL(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CU
     }
 }
 
+#ifndef GBXQ_TS_GROUPED
 struct Maps {
     CUtensorMap x, w, s, b;
 };
@@ -644,5 +701,125 @@ int TS_LAUNCH(const void* x, const uint32_t* w, const void* s, const void* b, co
     }
     return GBXQ_EINVAL_BITS;
 }
+
+#else  // GBXQ_TS_GROUPED: host side of the grouped launch
+
+template <int BITS, int BN>
+int launch_inst(const TsMaps& mp, const TsParams& p, int tiles, cudaStream_t st) {
+    constexpr size_t smem = Cfg<BITS, BN>::SMEM;
+    auto kern = TS_KERNEL<BITS, BN>;
+    static DeviceOnce configured;
+    if (configured.need()) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return check_cuda(e);
+        configured.done();
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)tiles, (unsigned)((p.M + BN - 1) / BN), (unsigned)(p.splits > 1 ? p.splits : 1));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = mmv_get_pdl_mode() > 0 ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mp, p);
+    count_launch();
+    return check_cuda(e);
+}
+
+template <int BITS>
+int launch_bn(int bn, const TsMaps& mp, const TsParams& p, int tiles, cudaStream_t st) {
+    switch (bn) {
+        case 16: return launch_inst<BITS, 16>(mp, p, tiles, st);
+        case 32: return launch_inst<BITS, 32>(mp, p, tiles, st);
+        case 64: return launch_inst<BITS, 64>(mp, p, tiles, st);
+        case 128: return launch_inst<BITS, 128>(mp, p, tiles, st);
+        default: return launch_inst<BITS, 256>(mp, p, tiles, st);
+    }
+}
+}  // namespace
+
+// The padded output width the split-K plan and the workspace of a grouped launch are sized for.
+int64_t gemm_ts_grouped_npad(const gbxq_segment* segs, int nseg) {
+    int64_t tiles = 0;
+    for (int i = 0; i < nseg; i++) tiles += (segs[i].N + kTileN - 1) / kTileN;
+    return tiles * kTileN;
+}
+
+// Returns GBXQ_EUNSUPPORTED (nothing enqueued) when the segments cannot share one launch.
+int launch_gemm_ts_grouped(const gbxq_segment* segs, int nseg, const void* x, int64_t M, int64_t K, void* workspace,
+                           size_t workspace_bytes, cudaStream_t st) {
+    if (nseg < 2 || nseg > 3 || M < 1 || !tma_encode_available()) return GBXQ_EUNSUPPORTED;
+    const int bits = segs[0].bits, gs = segs[0].group_size;
+    if (K % kStageK || (K * bits / 8) % 16 || ((K / gs) * 2) % 16 || ((uintptr_t)x & 15)) return GBXQ_EUNSUPPORTED;
+    const int bn = M <= 16 ? 16 : (M <= 32 ? 32 : (M <= 64 ? 64 : (M <= 128 ? 128 : 256)));
+    if ((M + bn - 1) / bn > 65535) return GBXQ_EUNSUPPORTED;
+    TsMaps mp;
+    TsParams p{};
+    const uint64_t words = (uint64_t)(K * bits / 32), G = (uint64_t)(K / gs);
+    const int swz = bits == 4 ? 64 : (bits == 2 ? 32 : (bits == 8 ? 128 : 0));
+    bool ok = encode_tensor_map_2d_sw(&mp.x, 0, x, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, kAtomK, (uint32_t)bn, 128);
+    int tiles = 0;
+    int64_t nsum = 0;
+    for (int i = 0; i < nseg; i++) {
+        const gbxq_segment& sg = segs[i];
+        if (sg.bits != bits || sg.group_size != gs || sg.N < 1) return GBXQ_EUNSUPPORTED;
+        if (((uintptr_t)sg.qweight | (uintptr_t)sg.scales | (uintptr_t)sg.biases) & 15) return GBXQ_EUNSUPPORTED;
+        if ((uintptr_t)sg.y & 1) return GBXQ_EUNSUPPORTED;
+        ok = ok && encode_tensor_map_2d_sw(&mp.w[i], 1, sg.qweight, words, (uint64_t)sg.N, words * 4, (uint32_t)(4 * bits), kTileN, swz);
+        ok = ok && encode_tensor_map_2d_sw(&mp.s[i], 0, sg.scales, G, (uint64_t)sg.N, G * 2, 8, kTileN, 0);
+        ok = ok && encode_tensor_map_2d_sw(&mp.b[i], 0, sg.biases, G, (uint64_t)sg.N, G * 2, 8, kTileN, 0);
+        p.tile0[i] = tiles;
+        p.seg_n[i] = sg.N;
+        p.seg_bias[i] = reinterpret_cast<const __nv_bfloat16*>(sg.bias);
+        p.seg_y[i] = reinterpret_cast<__nv_bfloat16*>(sg.y);
+        tiles += (int)((sg.N + kTileN - 1) / kTileN);
+        nsum += sg.N;
+    }
+    for (int i = nseg; i < 3; i++) {
+        mp.w[i] = mp.w[0];
+        mp.s[i] = mp.s[0];
+        mp.b[i] = mp.b[0];
+    }
+    p.tile0[nseg] = tiles;
+    if (!ok || tiles > 65535 * 32) return GBXQ_EUNSUPPORTED;
+    p.nseg = nseg;
+    p.M = M;
+    p.N = nsum;
+    p.K = K;
+    p.gs_shift = gs == 32 ? 5 : (gs == 64 ? 6 : 7);
+    p.splits = 1;
+    p.early_w = mmv_get_pdl_mode() >= 2 ? 1 : 0;
+    p.rotate = 0;
+    p.dbg = nullptr;
+    {
+        int sp, per;
+        size_t need;
+        gemm_split_plan(M, (int64_t)tiles * kTileN, K, &sp, &per, &need);
+        if (sp > 1 && workspace != nullptr && workspace_bytes >= need && !((uintptr_t)workspace & 15)) {
+            p.splits = sp;
+            p.kb_per_split = per;
+            p.cnt = reinterpret_cast<uint32_t*>(workspace);
+            p.ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + kCntBytes);
+            int64_t off = 0;
+            for (int i = 0; i < nseg; i++) {
+                p.seg_ws_off[i] = off;
+                off += (int64_t)sp * M * segs[i].N;
+            }
+        }
+    }
+    switch (bits) {
+        case 2: return launch_bn<2>(bn, mp, p, tiles, st);
+        case 3: return launch_bn<3>(bn, mp, p, tiles, st);
+        case 4: return launch_bn<4>(bn, mp, p, tiles, st);
+        case 6: return launch_bn<6>(bn, mp, p, tiles, st);
+        case 8: return launch_bn<8>(bn, mp, p, tiles, st);
+    }
+    return GBXQ_EINVAL_BITS;
+}
+
+#endif  // GBXQ_TS_GROUPED
 
 }  // namespace gbxq

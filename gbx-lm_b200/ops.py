@@ -170,10 +170,6 @@ def _qmm_grouped_op(
     if not x2.is_contiguous():
         x2 = x2.contiguous()
     m = x2.shape[0]
-    if m > 2:
-        # more rows than the one-launch decode kernel takes: one call per segment, each with its split-K scratch
-        # (gbxq_qmm_grouped's own per-segment fallback has none)
-        return [_qmm_impl(x, ws[i], scales[i], biases[i], bias[i], group_sizes[i], bits[i], 0) for i in range(nseg)]
     segs = (_lib.Segment * max(nseg, 1))()
     outs, keep = [], []
     for i in range(nseg):
@@ -194,7 +190,17 @@ def _qmm_grouped_op(
                                y.data_ptr(), n, bits[i], group_sizes[i])
     with torch.cuda.device(x.device):
         st = torch.cuda.current_stream().cuda_stream
-        rc = _lib.get().gbxq_qmm_grouped(segs, nseg, x2.data_ptr(), m, k, dt, st)
+        wsb, wsn = None, 0
+        if m > 4:  # decode batches / prefill: split-K scratch for the tensor-core GEMM (one grouped launch or per segment)
+            need = int(_lib.get().gbxq_grouped_workspace_bytes(segs, nseg, m, k, dt))
+            if need and os.environ.get("GBXQ_NO_SPLITK") != "1":
+                key = (x.device.index, st)
+                wsb = _WORKSPACES.get(key)
+                if wsb is None or wsb.numel() < need:
+                    wsb = torch.zeros((max(need, 8 << 20),), dtype=torch.uint8, device=x.device)
+                    _WORKSPACES[key] = wsb
+                wsn = wsb.numel()
+        rc = _lib.get().gbxq_qmm_grouped_ws(segs, nseg, x2.data_ptr(), m, k, dt, wsb.data_ptr() if wsb is not None else None, wsn, st)
     _lib.check(rc, "gbxq_qmm_grouped")
     return [y.reshape(*lead, y.shape[-1]) for y in outs]
 

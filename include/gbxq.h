@@ -136,6 +136,16 @@ typedef struct gbxq_segment {
 } gbxq_segment;
 int gbxq_qmm_grouped(const gbxq_segment* segs_host, int nseg, const void* x, int64_t M, int64_t K, int dtype,
                      void* stream);
+/*
+ * The same with scratch for the rows-of-x regime above the decode kernel (M > 4): segments that share bit width and
+ * group size then run as ONE launch of the tensor-core GEMM (gbxq_gemm_ts_grouped_sm100.cu), splitting K where the
+ * segments leave SMs idle; without a workspace (or with gbxq_qmm_grouped) such launches run unsplit.
+ * gbxq_grouped_workspace_bytes sizes the scratch; the rules of gbxq_qmm's workspace apply (first 16 KB zero once,
+ * owned by the stream).
+ */
+size_t gbxq_grouped_workspace_bytes(const gbxq_segment* segs_host, int nseg, int64_t M, int64_t K, int dtype);
+int gbxq_qmm_grouped_ws(const gbxq_segment* segs_host, int nseg, const void* x, int64_t M, int64_t K, int dtype,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Chain launch: an ordered list of decode-sized (M <= 4, bf16) quantized matmuls -- the QuantizedLinear forwards of

@@ -630,6 +630,53 @@ def test_qmm_grouped_matches_single_calls_and_oracle(cuda_device, M, gs):
             assert_close_to_truth(y, ref, f"grouped b{bits} N{N} M{M}")
 
 
+@pytest.mark.parametrize("bits,gs", [(4, 64), (2, 128), (8, 64), (3, 64)])
+def test_qmm_grouped_tensor_core_launch(cuda_device, bits, gs):
+    """Decode batches and prefill chunks of q|k|v / gate|up with one bit width: ONE launch of the TMEM-operand GEMM
+    (gbxq_gemm_ts_grouped_sm100.cu) for all segments -- against the oracle, against one call per segment (fp32
+    summation noise: the split-K plans differ), bitwise reproducible; mixed widths fall back to one call per segment."""
+    g = _ops()
+    from gbx_lm_b200 import ops
+
+    K = 2048
+    for M in (9, 40, 300):
+        for combo in ((512, 128, 128), (1024, 1000), (130, 64, 3)):
+            segs, raw = [], []
+            for i, N in enumerate(combo):
+                L = A.synth_layer(N, K, bits, gs, seed=11 * i + bits + N, with_bias=(i == 1))
+                raw.append(L)
+                segs.append(_Seg(layer_to_cuda(L, cuda_device), bits, gs))
+            xb = A.synth_x(M, K, seed=5 + M)
+            x = bf16_from_bits(xb, cuda_device)
+            n0 = ops.launch_count()
+            ys = g.quantized_matmul_grouped(x, segs)
+            assert ops.launch_count() - n0 == 1, (combo, M)
+            ys2 = g.quantized_matmul_grouped(x, segs)
+            plain = []
+            for sg in segs:  # the same segments without their bias
+                c = _Seg({"qweight": sg.qweight, "scales": sg.scales, "zeros": sg.zeros}, bits, gs)
+                plain.append(c)
+            ys0 = g.quantized_matmul_grouped(x, plain)
+            for sg, L, y, y2, y0, N in zip(segs, raw, ys, ys2, ys0, combo):
+                ref = A.quantized_matmul(xb, L["qweight"], L["scales"], L["zeros"], gs, bits, "bf16", "f64")
+                assert y.shape == (M, N) and torch.equal(y, y2)
+                assert_close_to_truth(y0, ref, f"grouped gemm_ts b{bits} N{N} M{M}", 1e-2)
+                # the bias is a second, separately rounded add on the rounded product (quantized_linear_gba.py:204-205):
+                # checked exactly (against the truth two roundings can stack to 2 bf16 ulps)
+                want = y0 if sg.bias is None else (y0.float() + sg.bias.float()).to(torch.bfloat16)
+                assert torch.equal(y, want)
+                single = g.quantized_matmul(x, sg.qweight, sg.scales, sg.zeros, True, gs, bits)
+                assert (y0.float() - single.float()).abs().max() <= 2.0 ** -6 * single.float().abs().max()
+    # mixed widths: per-segment launches, bitwise the single calls
+    segs = [_Seg(layer_to_cuda(A.synth_layer(256, K, b, gs, seed=b), cuda_device), b, gs) for b in (bits, 8 if bits != 8 else 4)]
+    x = bf16_from_bits(A.synth_x(20, K, seed=1), cuda_device)
+    n0 = ops.launch_count()
+    ys = g.quantized_matmul_grouped(x, segs)
+    assert ops.launch_count() - n0 == 2
+    for sg, y in zip(segs, ys):
+        assert torch.equal(y, g.quantized_matmul(x, sg.qweight, sg.scales, sg.zeros, True, gs, sg.bits))
+
+
 def test_qmm_grouped_validation(cuda_device):
     g = _ops()
     K = 256
