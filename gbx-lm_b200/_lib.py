@@ -29,6 +29,8 @@ EXPORTS = (
     "gbxq_qmm_stream",
     "gbxq_workspace_bytes",
     "gbxq_dequantize",
+    "gbxq_quantize",
+    "gbxq_quantize_rows",
     "gbxq_select_kernel",
     "gbxq_launch_count",
     "gbxq_set_option",
@@ -133,6 +135,10 @@ def get() -> ctypes.CDLL:
     lib.gbxq_workspace_bytes.argtypes = [i64, i64, i64, ci, ci, ci]
     lib.gbxq_dequantize.restype = ci
     lib.gbxq_dequantize.argtypes = [vp, vp, vp, vp, i64, i64, ci, ci, ci, vp]
+    lib.gbxq_quantize.restype = ci
+    lib.gbxq_quantize.argtypes = [vp, vp, vp, vp, i64, i64, ci, ci, ci, vp]
+    lib.gbxq_quantize_rows.restype = ci
+    lib.gbxq_quantize_rows.argtypes = [vp, vp, vp, vp, i64, i64, ci, ci, ci, i64, i64, i64, vp]
     lib.gbxq_select_kernel.restype = ci
     lib.gbxq_select_kernel.argtypes = [i64, i64, i64, ci, ci, ci]
     lib.gbxq_launch_count.restype = ctypes.c_uint64

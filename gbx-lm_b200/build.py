@@ -19,6 +19,7 @@ LIB = os.path.join(HERE, "libgbxq.so")
 SOURCES = [
     "gbxq_api.cu",
     "gbxq_dequant.cu",
+    "gbxq_quantize.cu",
     "gbxq_generic.cu",
     "gbxq_gemv.cu",
     "gbxq_skinny.cu",

@@ -601,10 +601,77 @@ def dequantize(w: torch.Tensor, scales: torch.Tensor, biases: torch.Tensor, grou
     return _dequantize_op(w, scales, biases, int(group_size), int(bits))
 
 
+def _check_quantize_args(w: torch.Tensor, group_size: int, bits: int) -> int:
+    if bits not in (2, 3, 4, 6, 8):
+        raise ValueError(f"[quantize] The requested number of bits {bits} is not supported. The supported bits are 2, 3, 4, 6 and 8.")
+    if group_size not in (32, 64, 128):
+        raise ValueError(f"[quantize] The requested group size {group_size} is not supported. The supported group sizes are 32, 64 and 128.")
+    if w.dim() < 2:
+        raise ValueError(f"[quantize] The matrix to be quantized must have at least 2 dimension but it has only {w.dim()}.")
+    if w.shape[-1] % group_size:
+        raise ValueError(f"[quantize] The last dimension of the matrix needs to be divisible by the quantization group size "
+                         f"{group_size}. However the provided matrix has shape {tuple(w.shape)}")
+    if w.dtype not in _DT:
+        raise ValueError(f"[quantize] Only real floating types can be quantized (bf16, f16, f32), got {w.dtype}")
+    _require_cuda(w)
+    return _DT[w.dtype]
+
+
+def quantize(w: torch.Tensor, group_size: int = 64, bits: int = 4):
+    """Drop-in for `mx.quantize` (gbxq_quantize): returns `(w_q, scales, biases)` with `w_q` uint32 `[..., K*bits/32]` and
+    `scales` / `biases` `[..., K/group_size]` in `w.dtype`, quantized along the last axis -- the call of
+    KVCache.to_quantized (gbx_lm/models/cache.py:251-263) and of QuantizedKVCache.update_and_fetch (cache.py:176-177).
+    Codes, scales and biases are bit-exact against the restatement of MLX's recipe (oracle/MLX_SPEC.md R6)."""
+    group_size, bits = int(group_size), int(bits)
+    dt = _check_quantize_args(w, group_size, bits)
+    k = w.shape[-1]
+    w = w.contiguous()
+    lead = tuple(w.shape[:-1])
+    rows = w.numel() // k
+    wq = torch.empty((*lead, k * bits // 32), dtype=torch.uint32, device=w.device)
+    scales = torch.empty((*lead, k // group_size), dtype=w.dtype, device=w.device)
+    biases = torch.empty_like(scales)
+    with torch.cuda.device(w.device):
+        rc = _lib.get().gbxq_quantize(w.data_ptr(), wq.data_ptr(), scales.data_ptr(), biases.data_ptr(), rows, k, bits,
+                                      group_size, dt, _stream())
+    _lib.check(rc, "gbxq_quantize")
+    return wq, scales, biases
+
+
+def quantize_into(w: torch.Tensor, out, offset: int, group_size: int = 64, bits: int = 4) -> None:
+    """`out[i][..., offset : offset + L, :] = mx.quantize(w, group_size, bits)[i]` for i = 0, 1, 2 in ONE launch
+    (gbxq_quantize_rows): w `[..., L, K]`, out = (codes, scales, biases) contiguous buffers `[..., capacity, *]` with the
+    same leading shape -- the cache write of QuantizedKVCache.update_and_fetch (gbx_lm/models/cache.py:176-180)."""
+    group_size, bits = int(group_size), int(bits)
+    dt = _check_quantize_args(w, group_size, bits)
+    oq, os_, ob = out
+    _require_cuda(w, oq, os_, ob)
+    _as_u32_ptr_tensor(oq)
+    if w.dim() < 2 or oq.dim() != w.dim():
+        raise ValueError("[quantize_into] w must be [..., L, K] and the outputs [..., capacity, *] of the same rank")
+    k, steps, cap = w.shape[-1], w.shape[-2], oq.shape[-2]
+    lead = tuple(w.shape[:-2])
+    if (tuple(oq.shape) != (*lead, cap, k * bits // 32) or tuple(os_.shape) != (*lead, cap, k // group_size)
+            or ob.shape != os_.shape or os_.dtype != w.dtype or ob.dtype != w.dtype):
+        raise ValueError(f"[quantize_into] outputs do not match w {tuple(w.shape)}: codes {tuple(oq.shape)}, scales "
+                         f"{tuple(os_.shape)} {os_.dtype}, biases {tuple(ob.shape)} {ob.dtype}")
+    if not (oq.is_contiguous() and os_.is_contiguous() and ob.is_contiguous()):
+        raise ValueError("[quantize_into] the output buffers must be contiguous")
+    if offset < 0 or offset + steps > cap:
+        raise ValueError(f"[quantize_into] rows [{offset}, {offset + steps}) do not fit a capacity of {cap}")
+    if steps == 0 or w.numel() == 0:
+        return
+    w = w.contiguous()
+    with torch.cuda.device(w.device):
+        rc = _lib.get().gbxq_quantize_rows(w.data_ptr(), oq.data_ptr(), os_.data_ptr(), ob.data_ptr(), w.numel() // k, k,
+                                           bits, group_size, dt, steps, cap, int(offset), _stream())
+    _lib.check(rc, "gbxq_quantize_rows")
+
+
 def select_kernel(m: int, n: int, k: int, bits: int, group_size: int, dtype: torch.dtype = torch.bfloat16) -> str:
     rc = _lib.get().gbxq_select_kernel(m, n, k, bits, group_size, _DT[dtype])
     _lib.check(min(rc, 0), "gbxq_select_kernel")
-    return {1: "generic", 2: "gemv", 3: "gemm", 4: "skinny", 5: "mmv", 6: "mmv8"}[rc]
+    return {1: "generic", 2: "gemv", 3: "gemm", 4: "skinny", 5: "mmv", 6: "mmv8", 7: "gemm_ts"}[rc]
 
 
 def set_pdl_mode(mode: int) -> None:

@@ -202,6 +202,31 @@ size_t gbxq_workspace_bytes(int64_t M, int64_t N, int64_t K, int bits, int group
 int gbxq_dequantize(const uint32_t* qweight, const void* scales, const void* biases, void* w_out,
                     int64_t N, int64_t K, int bits, int group_size, int dtype, void* stream);
 
+/*
+ * (qweight, scales, biases) = quantize(w): group-affine quantisation of a T matrix w[rows, K] into the layout above
+ * (codes uint32 [rows, K*bits/32], scales / biases T [rows, K/group_size]).
+ * Replaces mx.quantize(x, group_size=, bits=) where the reference quantises on the fly: the new keys / values of every
+ * step in QuantizedKVCache.update_and_fetch (gbx_lm/models/cache.py:176-177) and a whole dense cache in
+ * KVCache.to_quantized (cache.py:251-263); the consumers are the quantized_matmul calls of
+ * quantized_scaled_dot_product_attention (gbx_lm/models/base.py:85-93, gbxq_gather_qmm here).
+ * Per group, in fp32:  scale = max((max - min) / (2^bits - 1), 1e-7), signed so that the edge of larger magnitude is
+ * hit exactly (scale = edge / rint(edge / scale), bias = edge; bias = 0 when that rint is 0),
+ * code = clamp(rint((w - bias) / scale), 0, 2^bits - 1) from the unrounded scale / bias, which are then stored as T.
+ * K % group_size == 0; w 16-byte aligned.  rows == 0 is a no-op.
+ *
+ * gbxq_quantize_rows: the same with destination rows remapped -- source row r lands in row
+ *     (r / inner_rows) * out_outer_stride_rows + out_row_offset + r % inner_rows
+ * of the three outputs, i.e. the `inner_rows` new positions of every (batch, head) go to positions
+ * [out_row_offset, out_row_offset + inner_rows) of a cache of capacity out_outer_stride_rows
+ * (`self.keys[i][..., prev : self.offset, :] = keys[i]`, cache.py:178-180) without a staging copy.
+ * rows % inner_rows == 0 and out_row_offset + inner_rows <= out_outer_stride_rows, else GBXQ_ESHAPE.
+ */
+int gbxq_quantize(const void* w, uint32_t* qweight, void* scales, void* biases, int64_t rows, int64_t K, int bits,
+                  int group_size, int dtype, void* stream);
+int gbxq_quantize_rows(const void* w, uint32_t* qweight, void* scales, void* biases, int64_t rows, int64_t K, int bits,
+                       int group_size, int dtype, int64_t inner_rows, int64_t out_outer_stride_rows,
+                       int64_t out_row_offset, void* stream);
+
 /* Which kernel family GBXQ_KERNEL_AUTO picks for these arguments (a gbxq_kernel value, or <0). */
 int gbxq_select_kernel(int64_t M, int64_t N, int64_t K, int bits, int group_size, int dtype);
 

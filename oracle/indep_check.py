@@ -80,3 +80,36 @@ def qmm_row(x, words, scales, biases, group_size, bits, K):
         g = k // group_size
         acc += x[k] * (scales[g] * code_at(words, k, bits) + biases[g])
     return acc
+
+
+def _f32(v: float) -> float:
+    """one fp32 rounding of a double: for +, -, / of two fp32 operands the double result rounded to fp32 equals the
+    correctly rounded fp32 operation (53 >= 2 * 24 + 2 significand bits)"""
+    return struct.unpack("<f", struct.pack("<f", v))[0]
+
+
+def _rint(v: float) -> float:
+    f = float(int(v))  # toward zero
+    d = v - f
+    if abs(d) > 0.5 or (abs(d) == 0.5 and int(f) % 2 != 0):
+        f += 1.0 if v > 0 else -1.0
+    return f
+
+
+def quantize_group(ws, bits):
+    """R6 for ONE group: `ws` are the fp32 values of the group's elements (python floats holding T values).  Returns
+    (codes, scale, bias) with scale / bias still in fp32 -- the caller rounds them to T for storage.  Written from the
+    step list of R6 with scalar python arithmetic, one explicit fp32 rounding per operation."""
+    n_bins = float((1 << bits) - 1)
+    w_max, w_min = max(ws), min(ws)
+    scale = max(_f32(_f32(w_max - w_min) / n_bins), _f32(1e-7))
+    if abs(w_min) > abs(w_max):
+        edge = w_min
+    else:
+        edge, scale = w_max, -scale
+    q0 = _rint(_f32(edge / scale))
+    bias = 0.0
+    if q0 != 0:
+        scale, bias = _f32(edge / q0), edge
+    codes = [int(min(max(_rint(_f32(_f32(w - bias) / scale)), 0.0), n_bins)) for w in ws]
+    return codes, scale, bias

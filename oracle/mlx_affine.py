@@ -344,33 +344,38 @@ def gather_qmm(x, w, scales, biases, lhs_indices=None, rhs_indices=None, transpo
 
 
 # ----------------------------------------------------------------------------------------
-# quantize  (mx.quantize; only used to fabricate test weights -- SURVEY.md 8c.5.  The product
-# never needs to match it; kept for from_linear-style tests.)
+# quantize  (mx.quantize -- MLX_SPEC R6).  Used to fabricate test weights and as the checker of the device-side
+# quantiser (gbxq_quantize: the quantized KV cache, gbx_lm/models/cache.py:176-177,251-263).
 # ----------------------------------------------------------------------------------------
 
 
 def quantize(wf: np.ndarray, group_size: int = 64, bits: int = 4, dtype: str = "bf16"):
-    """Affine quantisation per MLX's recipe: returns (packed uint32, scales fp32-in-T, biases fp32-in-T)."""
+    """Affine quantisation per MLX's recipe (R6): returns (packed uint32, scales, biases), the statistics as fp32 arrays
+    holding T values.  Everything is evaluated in fp32, one rounding per operation; the codes come from the UNROUNDED
+    fp32 scale / bias and only the stored statistics are cast to T.  `wf` is any [..., K] array of T values."""
     _check_bits_gs(bits, group_size)
     wf = _round_to(np.asarray(wf, dtype=np.float32), dtype)
-    N, K = wf.shape
+    if wf.ndim < 2:
+        raise ValueError("[quantize] the matrix to be quantized must have at least 2 dimensions")
+    lead, K = wf.shape[:-1], wf.shape[-1]
     if K % group_size:
-        raise ValueError("K must be a multiple of group_size")
-    g = wf.reshape(N, K // group_size, group_size)
-    n_bins = float((1 << bits) - 1)
+        raise ValueError("[quantize] the last dimension must be divisible by the group size")
+    g = wf.reshape(-1, K // group_size, group_size)
+    N = g.shape[0]
+    n_bins = np.float32((1 << bits) - 1)
     w_max = g.max(-1)
     w_min = g.min(-1)
     mask = np.abs(w_min) > np.abs(w_max)
-    scales = np.maximum((w_max - w_min) / n_bins, 1e-7)
+    scales = np.maximum((w_max - w_min) / n_bins, np.float32(1e-7))
     scales = np.where(mask, scales, -scales)
     edge = np.where(mask, w_min, w_max)
     q0 = np.rint(edge / scales)
-    scales = np.where(q0 != 0, edge / np.where(q0 != 0, q0, 1), scales)
-    biases = np.where(q0 == 0, 0.0, edge)
-    scales = _round_to(scales, dtype)
-    biases = _round_to(biases, dtype)
+    scales = np.where(q0 != 0, edge / np.where(q0 != 0, q0, np.float32(1)), scales).astype(np.float32)
+    biases = np.where(q0 == 0, np.float32(0), edge).astype(np.float32)
     q = np.clip(np.rint((g - biases[..., None]) / scales[..., None]), 0, n_bins).astype(np.uint8)
-    return pack_codes(q.reshape(N, K), bits), scales, biases
+    packed = pack_codes(q.reshape(N, K), bits)
+    return (packed.reshape(*lead, packed.shape[-1]), _round_to(scales, dtype).reshape(*lead, K // group_size),
+            _round_to(biases, dtype).reshape(*lead, K // group_size))
 
 
 # ----------------------------------------------------------------------------------------
