@@ -11,7 +11,11 @@
 //     q0 = rint(edge / scale);  if (q0 != 0) { scale = edge / q0;  bias = edge; } else bias = 0
 //     code = clamp(rint((w - bias) / scale), 0, 2^bits - 1)         <- from the UNROUNDED fp32 scale / bias
 //     scales[g] = T(scale), biases[g] = T(bias)
-// Codes, scales and biases are bit-exact against the restatement (tests/test_gpu_quantize.py).
+// Codes, scales and biases are bit-exact against the restatement (tests/test_gpu_quantize.py).  The per-element
+// quotient is the IEEE one computed from ONE reciprocal per lane (two FMAs of correction), rint + conversion are a
+// magic-number add: the first version (a full division, FRND and F2I per element, no load ahead) ran at 0.19-0.22 of
+// the HBM roofline on large inputs, bound by the quarter-rate pipe and by one load in flight per warp
+// (profiles/r04a_quantbench.txt).
 //
 // HBM-bound byte work: reads sizeof(T) bytes and writes bits/8 bytes per element (+ 2 * sizeof(T) per group).  The
 // problem is flat: groups never cross rows (K % group_size == 0) and rows of codes are whole words (K % 32 == 0), so
@@ -34,18 +38,29 @@ __device__ __forceinline__ int64_t map_row(const RowMap& m, int64_t r) {
     return o * m.outer_stride + m.offset + (r - o * m.inner);
 }
 
-__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
-    const uint4 u = *reinterpret_cast<const uint4*>(p);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+// raw registers of a lane's 8 elements: loaded one chunk AHEAD of their use (the conversion to fp32 happens at use, so
+// that the in-order issue does not stall on the load it is meant to overlap)
+template <typename T> struct Raw { uint4 a; };
+template <> struct Raw<float> { uint4 a, b; };
+
+template <typename T> __device__ __forceinline__ void load_raw(const T* p, Raw<T>& r) {
+    r.a = __ldg(reinterpret_cast<const uint4*>(p));
+    if constexpr (sizeof(T) == 4) r.b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+}
+template <typename T> __device__ __forceinline__ void zero_raw(Raw<T>& r) {
+    r.a = make_uint4(0, 0, 0, 0);
+    if constexpr (sizeof(T) == 4) r.b = make_uint4(0, 0, 0, 0);
+}
+__device__ __forceinline__ void to_f32x8(const Raw<__nv_bfloat16>& r, float (&v)[8]) {
+    const uint32_t w[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         v[2 * i] = __uint_as_float(w[i] << 16);
         v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
     }
 }
-__device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
-    const uint4 u = *reinterpret_cast<const uint4*>(p);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+__device__ __forceinline__ void to_f32x8(const Raw<__half>& r, float (&v)[8]) {
+    const uint32_t w[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
@@ -53,11 +68,21 @@ __device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
         v[2 * i + 1] = __high2float(h);
     }
 }
-__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
-    const float4 a = reinterpret_cast<const float4*>(p)[0];
-    const float4 b = reinterpret_cast<const float4*>(p)[1];
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+__device__ __forceinline__ void to_f32x8(const Raw<float>& r, float (&v)[8]) {
+    v[0] = __uint_as_float(r.a.x); v[1] = __uint_as_float(r.a.y); v[2] = __uint_as_float(r.a.z); v[3] = __uint_as_float(r.a.w);
+    v[4] = __uint_as_float(r.b.x); v[5] = __uint_as_float(r.b.y); v[6] = __uint_as_float(r.b.z); v[7] = __uint_as_float(r.b.w);
+}
+
+// destination index of flat index `i` (a word of codes or a group) whose rows hold `per_row` of them
+__device__ __forceinline__ int64_t map_index(const RowMap& m, int64_t i, int64_t per_row, bool small) {
+    if (small) {  // everything fits 32 bits: a 32-bit division is a fraction of the 64-bit one
+        const uint32_t r = (uint32_t)i / (uint32_t)per_row;
+        const uint32_t o = r / (uint32_t)m.inner;
+        return ((int64_t)o * m.outer_stride + m.offset + (r - o * (uint32_t)m.inner)) * per_row +
+               ((uint32_t)i - r * (uint32_t)per_row);
+    }
+    const int64_t r = i / per_row;
+    return map_row(m, r) * per_row + (i - r * per_row);
 }
 
 constexpr int kWarps = 8;
@@ -74,19 +99,26 @@ __global__ void __launch_bounds__(kWarps * 32) quantize_kernel(const T* __restri
     const int64_t gpr = K / gs;         // groups per row
     const int64_t total_words = total / 32 * BITS;
     const int seg = gs >> 3;            // lanes per group: 4, 8, 16
-    const float nb = (float)((1 << BITS) - 1);
+    constexpr int NB = (1 << BITS) - 1;
+    const float nb = (float)NB;
     const bool dense = map.inner <= 0;
+    const bool small = total_words < (int64_t(1) << 31) && total < (int64_t(1) << 31);
+    const int64_t stride = (int64_t)gridDim.x * kWarps;
 
-    for (int64_t c = (int64_t)blockIdx.x * kWarps + warp; c < nchunks; c += (int64_t)gridDim.x * kWarps) {
+    int64_t c = (int64_t)blockIdx.x * kWarps + warp;
+    Raw<T> cur, nxt;
+    zero_raw(cur);
+    if (c < nchunks && (c << 8) + (lane << 3) < total) load_raw(w + (c << 8) + (lane << 3), cur);
+    for (; c < nchunks; c += stride) {
         const int64_t e0 = (c << 8) + (lane << 3);
         const bool live = e0 < total;  // total % 8 == 0: a lane's 8 elements are all inside or all outside
-        float v[8];
-        if (live) {
-            load8(w + e0, v);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; i++) v[i] = 0.f;
+        {
+            const int64_t en = e0 + (stride << 8);  // the chunk of the next iteration, requested before this one is used
+            zero_raw(nxt);
+            if (en < total) load_raw(w + en, nxt);
         }
+        float v[8];
+        to_f32x8(cur, v);  // dead lanes hold zeros
         float mx = v[0], mn = v[0];
 #pragma unroll
         for (int i = 1; i < 8; i++) {
@@ -108,12 +140,23 @@ __global__ void __launch_bounds__(kWarps * 32) quantize_kernel(const T* __restri
             scale = __fdiv_rn(edge, q0);
             bias = edge;
         }
+        // (w - bias) / scale, correctly rounded, without a division per element: with r = RN(1 / scale),
+        // q1 = RN(d * r), rem = d - q1 * scale (exact in one FMA), q = RN(q1 + rem * r) is the IEEE quotient (Markstein;
+        // |scale| >= ~5e-8 keeps r and the quotients that can reach a rounding boundary of rint() in the normal range).
+        // rint() and the float -> int conversion are one add of 1.5 * 2^23 (ulp 1, ties to even; |q| < 2^22 always:
+        // every |w - bias| <= max - min <= (2^bits) * |scale|), the clamp is an integer min / max.
+        const float r = __frcp_rn(scale);
+        const float nscale = -scale;
         uint64_t pack = 0;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            float t = rintf(__fdiv_rn(__fsub_rn(v[i], bias), scale));
-            t = fminf(fmaxf(t, 0.f), nb);
-            pack |= (uint64_t)(uint32_t)t << (i * BITS);
+            const float d = __fsub_rn(v[i], bias);
+            const float q1 = __fmul_rn(d, r);
+            const float rem = __fmaf_rn(q1, nscale, d);
+            const float qq = __fmaf_rn(rem, r, q1);
+            int code = (int)__float_as_uint(__fadd_rn(qq, 12582912.0f)) - 0x4B400000;
+            code = min(max(code, 0), NB);
+            pack |= (uint64_t)(uint32_t)code << (i * BITS);
         }
         // the lane's 8 codes are bytes [lane * BITS, (lane + 1) * BITS) of the chunk's LSB-first stream
         if constexpr (BITS == 8) {
@@ -127,11 +170,8 @@ __global__ void __launch_bounds__(kWarps * 32) quantize_kernel(const T* __restri
             for (int b = 0; b < BITS; b++) stage[lane * BITS + b] = (uint8_t)(pack >> (8 * b));
         }
         if (live && (lane & (seg - 1)) == 0) {
-            int64_t g = e0 / gs;
-            if (!dense) {
-                const int64_t r = g / gpr;
-                g = map_row(map, r) * gpr + (g - r * gpr);
-            }
+            int64_t g = small ? (int64_t)((uint32_t)e0 / (uint32_t)gs) : e0 / gs;
+            if (!dense) g = map_index(map, g, gpr, small);
             scales[g] = from_f32<T>(scale);
             biases[g] = from_f32<T>(bias);
         }
@@ -141,15 +181,25 @@ __global__ void __launch_bounds__(kWarps * 32) quantize_kernel(const T* __restri
             int64_t wi = w0 + j;
             if (wi < total_words) {
                 const uint32_t word = reinterpret_cast<const uint32_t*>(stage)[j];
-                if (!dense) {
-                    const int64_t r = wi / wpr;
-                    wi = map_row(map, r) * wpr + (wi - r * wpr);
-                }
+                if (!dense) wi = map_index(map, wi, wpr, small);
                 q[wi] = word;
             }
         }
         __syncwarp();
+        cur = nxt;
     }
+}
+
+// resident CTAs per SM of this instantiation (registers decide), asked once per process
+template <int BITS, typename T> int ctas_per_sm() {
+    static std::atomic<int> cached{0};
+    int n = cached.load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, quantize_kernel<BITS, T>, kWarps * 32, 0) != cudaSuccess || n < 1)
+            n = 4;
+        cached.store(n, std::memory_order_relaxed);
+    }
+    return n;
 }
 
 template <int BITS, typename T>
@@ -157,7 +207,7 @@ int launch_t(const void* w, uint32_t* q, void* s, void* b, int64_t total, int64_
              cudaStream_t st) {
     const int64_t nchunks = (total + 255) >> 8;
     int64_t blocks = (nchunks + kWarps - 1) / kWarps;
-    const int64_t cap = (int64_t)device_sm_count() * 8;  // 8 CTAs of 256 threads per SM, grid-stride beyond
+    const int64_t cap = (int64_t)device_sm_count() * ctas_per_sm<BITS, T>();  // one resident wave, grid-stride beyond
     if (blocks > cap) blocks = cap;
     quantize_kernel<BITS, T><<<(unsigned)blocks, kWarps * 32, 0, st>>>((const T*)w, q, (T*)s, (T*)b, total, K, gs, map);
     count_launch();

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Device-side mx.quantize (gbxq_quantize / gbxq_quantize_rows): microseconds per call, algorithmic GB/s
 (sizeof(T) read + bits/8 written per element + 2 * sizeof(T) per group) and fraction of the measured HBM peak, for the
-shapes the quantized KV cache produces (gbx_lm/models/cache.py:176-177,251-263).   python tools/quantbench.py"""
+shapes the quantized KV cache produces (gbx_lm/models/cache.py:176-177,251-263).   python tools/quantbench.py [case substring]"""
 import json
 import os
 import sys
@@ -23,7 +23,10 @@ CASES = (
     ("to_quantized: 8 heads x 32768 x 128", (1, 8, 32768, 128), False),
     ("weight matrix 4096 x 14336", (4096, 14336), False),
 )
+ONLY = sys.argv[1] if len(sys.argv) > 1 else ""  # substring filter on the case name
 for name, shape, into in CASES:
+    if ONLY not in name:
+        continue
     for bits, gs in ((8, 64), (4, 64), (3, 64)):
         w = torch.randn(shape, device=dev).to(torch.bfloat16)
         if into:
