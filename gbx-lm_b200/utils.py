@@ -190,57 +190,51 @@ def load(path: Union[str, Path], model_config: dict = {}, lazy: bool = False, de
 
 
 # ------------------------------------------------------------------------------------------ writer
+def _nbytes(t: torch.Tensor) -> int:
+    return t.numel() * t.element_size()
+
+
 def make_shards(weights: dict, max_file_size_gb: int = MAX_FILE_SIZE_GB) -> list:
-    """gbx_lm/utils.py:967-988."""
-    max_file_size_bytes = max_file_size_gb << 30
-    shards = []
-    shard, shard_size = {}, 0
-    for k, v in weights.items():
-        nbytes = v.numel() * v.element_size()
-        if shard_size + nbytes > max_file_size_bytes:
-            shards.append(shard)
-            shard, shard_size = {}, 0
-        shard[k] = v
-        shard_size += nbytes
-    shards.append(shard)
+    """The on-disk split of gbx_lm/utils.py:967-988: tensors in insertion order, a tensor that would take the current
+    file over the cap opens the next one.  (The reference also emits an EMPTY first shard when the very first tensor is
+    over the cap; no empty file is written here.)"""
+    cap = max_file_size_gb << 30
+    shards, used = [{}], 0
+    for name, t in weights.items():
+        if shards[-1] and used + _nbytes(t) > cap:
+            shards.append({})
+            used = 0
+        shards[-1][name] = t
+        used += _nbytes(t)
     return shards
 
 
 def save_weights(save_path: Union[str, Path], weights: Dict[str, torch.Tensor], *, donate_weights: bool = False,
                  max_file_size_gb: int = MAX_FILE_SIZE_GB) -> None:
-    """gbx_lm/utils.py:1055-1104: shards + index, metadata {"format": "mlx"}."""
+    """The layout `load_model` (and gbx_lm/utils.py:1055-1104) expects: `model.safetensors`, or
+    `model-0000i-of-0000n.safetensors` when the split has n > 1 files, each with metadata {"format": "mlx"}, plus
+    `model.safetensors.index.json` = {"metadata": {"total_size"}, "weight_map": name -> file, sorted by name}."""
     from safetensors.torch import save_file
 
-    save_path = Path(save_path)
-    save_path.mkdir(parents=True, exist_ok=True)
+    out = Path(save_path)
+    out.mkdir(parents=True, exist_ok=True)
     shards = make_shards(weights, max_file_size_gb)
-    shards_count = len(shards)
-    shard_file_format = "model-{:05d}-of-{:05d}.safetensors" if shards_count > 1 else "model.safetensors"
-    total_size = sum(v.numel() * v.element_size() for v in weights.values())
-    index_data = {"metadata": {"total_size": total_size}, "weight_map": {}}
+    n = len(shards)
+    index = {"metadata": {"total_size": sum(_nbytes(t) for t in weights.values())}, "weight_map": {}}
     if donate_weights:
-        weights.clear()
-        del weights
-    for i in range(len(shards)):
-        shard = shards[i]
-        shards[i] = None
-        shard_name = shard_file_format.format(i + 1, shards_count)
-        save_file({k: v.contiguous().cpu() for k, v in shard.items()}, str(save_path / shard_name), metadata={"format": "mlx"})
-        for weight_name in shard.keys():
-            index_data["weight_map"][weight_name] = shard_name
-        del shard
-    index_data["weight_map"] = {k: index_data["weight_map"][k] for k in sorted(index_data["weight_map"])}
-    with open(save_path / "model.safetensors.index.json", "w") as f:
-        json.dump(index_data, f, indent=4)
+        weights.clear()  # the shards hold the only references from here on
+    for i in range(1, n + 1):
+        shard = shards.pop(0)  # dropped after the write, so that a donated checkpoint is freed file by file
+        fname = f"model-{i:05d}-of-{n:05d}.safetensors" if n > 1 else "model.safetensors"
+        save_file({k: v.contiguous().cpu() for k, v in shard.items()}, str(out / fname), metadata={"format": "mlx"})
+        index["weight_map"].update(dict.fromkeys(shard, fname))
+    index["weight_map"] = dict(sorted(index["weight_map"].items()))
+    (out / "model.safetensors.index.json").write_text(json.dumps(index, indent=4))
 
 
 def save_config(config: dict, config_path: Union[str, Path]) -> None:
-    """gbx_lm/utils.py:1107-1127."""
-    config = dict(config)
-    config.pop("_name_or_path", None)
-    config = dict(sorted(config.items()))
-    with open(config_path, "w") as fid:
-        json.dump(config, fid, indent=4)
+    """gbx_lm/utils.py:1107-1127: keys sorted, `_name_or_path` dropped (from the written copy only)."""
+    Path(config_path).write_text(json.dumps({k: config[k] for k in sorted(config) if k != "_name_or_path"}, indent=4))
 
 
 def write_synthetic_checkpoint(path: Union[str, Path], dims, strategy: Optional[dict], seed: int = 0,

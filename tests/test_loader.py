@@ -111,8 +111,38 @@ def test_strategy_missing_entry_raises(tiny_ckpt):
 def test_make_shards_counts():
     w = {f"w{i}": torch.zeros(1 << 18, dtype=torch.float32) for i in range(8)}  # 1 MiB each
     assert len(utils.make_shards(w, max_file_size_gb=5)) == 1
-    shards = utils.make_shards(w, max_file_size_gb=0)  # 0 GiB cap -> one tensor per shard (+ leading empty)
-    assert sum(len(s) for s in shards) == 8
+    shards = utils.make_shards(w, max_file_size_gb=0)  # 0 GiB cap -> one tensor per shard, no empty one
+    assert [len(s) for s in shards] == [1] * 8
+    assert utils.make_shards({}) == [{}]
+
+
+def test_multi_shard_layout_round_trip(tmp_path):
+    """n > 1 files: names model-0000i-of-0000n.safetensors, {"format": "mlx"} metadata, a name-sorted index whose
+    total_size is the byte count, no empty file, every tensor back bit for bit; config written sorted without
+    `_name_or_path` and without touching the caller's dict (gbx_lm/utils.py:967-988,1055-1127)."""
+    from safetensors import safe_open
+
+    gen = torch.Generator().manual_seed(0)
+    w = {f"model.layers.{i}.w": torch.randn((64, 64), generator=gen).to(torch.bfloat16) for i in (2, 0, 1)}
+    w["model.layers.0.qweight"] = torch.arange(256, dtype=torch.int32).view(torch.uint32).reshape(16, 16)
+    keep = dict(w)
+    utils.save_weights(tmp_path, w, max_file_size_gb=0, donate_weights=True)
+    assert w == {}                                               # donated
+    files = sorted(p.name for p in tmp_path.glob("*.safetensors"))
+    assert files == [f"model-{i:05d}-of-00004.safetensors" for i in range(1, 5)]
+    idx = json.load(open(tmp_path / "model.safetensors.index.json"))
+    assert list(idx["weight_map"]) == sorted(keep) and set(idx["weight_map"].values()) == set(files)
+    assert idx["metadata"]["total_size"] == sum(t.numel() * t.element_size() for t in keep.values())
+    for name, fname in idx["weight_map"].items():
+        with safe_open(str(tmp_path / fname), framework="pt") as f:
+            assert f.metadata() == {"format": "mlx"} and list(f.keys()) == [name]
+            got = f.get_tensor(name)
+        a, b = (got.view(torch.int32), keep[name].view(torch.int32)) if got.dtype == torch.uint32 else (got, keep[name])
+        assert torch.equal(a, b)
+    cfg = {"z": 1, "_name_or_path": "x", "a": {"k": 2}}
+    utils.save_config(cfg, tmp_path / "config.json")
+    assert "_name_or_path" in cfg
+    assert list(json.load(open(tmp_path / "config.json"))) == ["a", "z"]
 
 
 def test_workload_bytes_match_baseline_md():
