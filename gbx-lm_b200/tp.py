@@ -130,8 +130,9 @@ class OneShotAllReduce:
         self.capacity = capacity_elems
         self.buf = symm.empty((capacity_elems,), dtype=dtype, device=device)
         self.hdl = symm.rendezvous(self.buf, self.group.group_name)
-        # + 2: device-resident sequence number and CTA counter (seq = 0 mode: CUDA-graph replayable)
-        self.flags = symm.empty((self.world * _lib.AR_MAX_CTAS + 2,), dtype=torch.int32, device=device)
+        # control words behind the flags (include/gbxq.h: world * GBXQ_AR_MAX_CTAS + 3 entries are needed): +0 the
+        # device-resident sequence number (seq = 0 mode: CUDA-graph replayable), +1 the CTA counter, +2 the time-out word
+        self.flags = symm.empty((self.world * _lib.AR_MAX_CTAS + 4,), dtype=torch.int32, device=device)
         self.flags.zero_()
         self.fhdl = symm.rendezvous(self.flags, self.group.group_name)
         bufs = [self.hdl.buffer_ptrs[r] for r in range(self.world)]
@@ -146,6 +147,12 @@ class OneShotAllReduce:
     # 40 MB partial goes to NCCL's bandwidth-optimal rings (r03e: Qwen2.5-32B prefill of 4096 tokens at tp4 took 1165 ms
     # with every message on the one-shot kernel, 5x the single-GPU time).
     MAX_BYTES = 1 << 20
+
+    def timed_out(self) -> bool:
+        """True once a wait for a peer gave up (4 s): results of that call are undefined (synchronises)."""
+        from . import _lib
+
+        return bool(self.flags[self.world * _lib.AR_MAX_CTAS + 2].item())
 
     def fits(self, y: torch.Tensor) -> bool:
         nbytes = y.numel() * y.element_size()
