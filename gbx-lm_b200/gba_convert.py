@@ -16,7 +16,7 @@ What the reference does when it loads an ORIGINAL GreenBitAI "GBA" checkpoint wi
     (the fp16 values of the double-quant expansion are truncated to bf16 here, as in the reference)   utils.py:837-843
 
 `convert_gba_weights` returns a state dict in exactly the layout `gbx_lm_b200.utils.load_model` (and gba2mlx's output)
-uses; `q_perm` / `channel_scale` are carried along untouched (unused by the forward: quantized_linear_gba.py:187-192).
+uses -- `load_model(..., is_conversion=True)` calls it right after reading the files; `q_perm` / `channel_scale` are carried along untouched (unused by the forward: quantized_linear_gba.py:187-192).
 """
 from __future__ import annotations
 
@@ -82,4 +82,23 @@ def convert_gba_weights(weights: Dict[str, torch.Tensor], group_size_of=None) ->
         if any(s in k for s in ("norm.weight", "bias", "gate.weight", "lm_head", "embed_tokens", "channel_scale")):
             v = v.to(torch.bfloat16)
         out[k] = v
+    return out
+
+
+def expand_statistics(weights: Dict[str, torch.Tensor], group_size_of=None) -> Dict[str, torch.Tensor]:
+    """A checkpoint ALREADY in the MLX orientation that still carries double-quantised statistics (the reference's
+    `use_double_quantization and not is_conversion` case: `prepare_scales_zeros` without `post_processing_and_release`,
+    gbx_lm/utils.py:864-868): only the second-level codes are expanded to `scales` / `zeros`; no transpose, no sign flip."""
+    out = {k: v for k, v in weights.items() if not any(k.endswith("." + leaf) for leaf in DQ_LEAVES)}
+    for k, st in weights.items():
+        if not k.endswith(".qstatistic"):
+            continue
+        m = k.rsplit(".", 1)[0]
+        gs = group_size_of(m) if group_size_of is not None else 64
+        n = weights[m + ".qweight"].shape[0]
+        scales, zeros = expand_double_quant(st, weights[m + ".qzeros_zeros"], weights[m + ".qzeros_scales"],
+                                            weights[m + ".qscales_zeros"], weights[m + ".qscales_scales"],
+                                            st.shape[0] * gs, n, gs)
+        out[m + ".scales"] = scales.to(torch.bfloat16)
+        out[m + ".zeros"] = zeros.to(torch.bfloat16)
     return out

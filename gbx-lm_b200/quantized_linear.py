@@ -23,6 +23,23 @@ PROJ_KEYS = (  # match order of quantized_linear_gba.py:261 (first substring hit
 )
 
 
+def strategy_params(name: str, strategy: Optional[dict], bits: int, group_size: int):
+    """(bits, group_size) of the QuantizedLinear called `name` (`model.layers.<i>....<proj>`): its entry of
+    `quant_strategy.json`'s "measurement" table, matched as `reinit_module` matches it (quantized_linear_gba.py:258-272),
+    or the uniform defaults when there is no strategy (:278-281).  KeyError when the block has no entry for it."""
+    if strategy is None:
+        return bits, group_size
+    block = strategy["model.layers.{}".format(name.split(".")[2])]
+    for key in PROJ_KEYS:
+        if key in name:
+            if "shared_expert" in name:
+                key = "moe_shared_expert_" + key
+            if key in block:
+                b = block[key]["bits"][0]
+                return b, block[key]["group_size"][str(b)]
+    raise KeyError(f"quant_strategy.json has no entry for {name}")
+
+
 class QuantizedLinear(nn.Module):
     """y = x . dequant(qweight)^T (+ bias) with MLX group-affine packed weights.
 

@@ -133,10 +133,19 @@ def load_model(
         assert quantization["group_size"] in [32, 64, 128], \
             f"The group size value ({group_size}) must be 32, 64 or 128."
     if is_conversion or use_double_quantization:
-        raise NotImplementedError(
-            "GBA->MLX conversion (transposes, double-quant expansion, zero negation) is outside the hot path "
-            "(SURVEY.md 8f rank 4); load a checkpoint already converted by gba2mlx"
-        )
+        # an original GBA checkpoint (K-major qweight / statistics, subtractive zeros, optionally double-quantised
+        # statistics): brought to the layout of the path on the host, before any module sees it -- the reference's
+        # transposes (utils.py:828-838), `prepare_scales_zeros` and `post_processing_and_release` (:864-873)
+        from .gba_convert import convert_gba_weights, expand_statistics
+        from .quantized_linear import strategy_params
+
+        def gs_of(mod_name: str) -> int:
+            return strategy_params(mod_name, strategy, quantization["bits"], quantization["group_size"])[1]
+
+        weights = convert_gba_weights(weights, gs_of) if is_conversion else expand_statistics(weights, gs_of)
+        for k in [k for k in weights if k.endswith(".q_perm")]:
+            weights[k] = weights[k].reshape(1, 1, -1)  # quantized_linear_gba.py:157-158
+        use_double_quantization = False  # plain scales / zeros from here on
     # scales / zeros -> bf16 (utils.py:841-843)
     for k, v in weights.items():
         if "scale" in k or "zeros" in k:

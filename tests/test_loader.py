@@ -194,3 +194,65 @@ def test_tp_illegal_row_split():
         tpmod.check_row_split(2048, 4, 128, 32)  # 64 codes per rank < one group of 128
     tpmod.check_row_split(27648, 4, 128, 8)  # Qwen2.5-32B down_proj at tp8: 3456 = 27 groups -> legal
     tpmod.check_row_split(28672, 4, 64, 8)   # Llama-3-70B down_proj at tp8: 3584 = 56 groups -> legal
+
+
+def test_load_model_converts_a_gba_checkpoint(tiny_ckpt, tmp_path):
+    """`load_model(..., is_conversion=True)` on an original GBA layout (K-major qweight / scales / zeros, subtractive fp16
+    zeros, a q_perm vector; gbx_lm/utils.py:828-843,864-873) gives the same modules as loading the converted checkpoint."""
+    import shutil
+
+    from safetensors.torch import load_file
+
+    d, dims, strat = tiny_ckpt
+    mlx_w = load_file(str(d / "model.safetensors"))
+    gba = {}
+    for k, v in mlx_w.items():
+        if k.endswith(".qweight"):
+            gba[k] = v.view(torch.int32).t().contiguous()
+        elif k.endswith(".scales"):
+            gba[k] = v.t().contiguous().to(torch.float16)
+        elif k.endswith(".zeros"):
+            gba[k] = (-v.float()).t().contiguous().to(torch.float16)
+        else:
+            gba[k] = v.to(torch.float16) if v.is_floating_point() else v
+    perm_key = "model.layers.0.mlp.down_proj.q_perm"
+    gba[perm_key] = torch.arange(dims.inter, dtype=torch.int16)
+    utils.save_weights(tmp_path, gba)
+    for f in ("config.json", "quant_strategy.json"):
+        shutil.copy(d / f, tmp_path / f)
+    ref, _ = utils.load_model(d, device="cpu")
+    got, _ = utils.load_model(tmp_path, device="cpu", is_conversion=True)
+    n = 0
+    for (name, a), (_, b) in zip(ref.named_modules(), got.named_modules()):
+        if isinstance(a, QuantizedLinear):
+            assert (a.bits, a.group_size) == (b.bits, b.group_size)
+            assert torch.equal(a.qweight.view(torch.int32), b.qweight.view(torch.int32)), name
+            # synthetic scales / zeros are bf16 values; fp16 holds them exactly unless they are fp16-subnormal
+            assert torch.allclose(a.scales.float(), b.scales.float(), rtol=0, atol=1e-7) and b.scales.dtype == torch.bfloat16
+            assert torch.allclose(a.zeros.float(), b.zeros.float(), rtol=0, atol=1e-7)
+            n += 1
+    assert n == 7 * dims.layers
+    assert dict(got.named_buffers())[perm_key].shape == (1, 1, dims.inter)
+    assert torch.equal(dict(ref.named_parameters())["model.norm.weight"], dict(got.named_parameters())["model.norm.weight"])
+
+
+def test_expand_statistics_of_an_mlx_oriented_double_quant_checkpoint():
+    """`use_double_quantization and not is_conversion` (gbx_lm/utils.py:864-868): the statistics are expanded in place
+    of the codes, nothing is transposed or negated; strategy_params finds the group size the expansion needs."""
+    from gbx_lm_b200 import gba_convert as G
+    from gbx_lm_b200.quantized_linear import strategy_params
+    from tests.test_gba_convert import _gba_layer
+
+    n, k, bits, gs = 64, 256, 4, 64
+    layer, q, s_bf, z_bf = _gba_layer(n, k, bits, gs, seed=1, double_quant=True)
+    p = "model.layers.3.mlp.up_proj."
+    w = {p + leaf: t for leaf, t in layer.items()}
+    w[p + "qweight"] = w[p + "qweight"].t().contiguous()          # already [N, K*bits/32]
+    strategy = {"model.layers.3": {"up_proj": {"bits": [bits], "group_size": {str(bits): gs}}}}
+    assert strategy_params(p[:-1], strategy, 2, 128) == (bits, gs) and strategy_params(p[:-1], None, 2, 128) == (2, 128)
+    with pytest.raises(KeyError):
+        strategy_params("model.layers.3.mlp.down_proj", strategy, 2, 128)
+    out = G.expand_statistics(w, lambda m: strategy_params(m, strategy, 2, 128)[1])
+    assert set(out) == {p + "qweight", p + "scales", p + "zeros"}
+    assert torch.equal(out[p + "qweight"], w[p + "qweight"])
+    assert np.array_equal(out[p + "scales"].float().numpy(), s_bf.T) and np.array_equal(out[p + "zeros"].float().numpy(), z_bf.T)
