@@ -196,3 +196,12 @@ def test_stream_plan_blob_invariants():
                 assert stages == info.stages and slot_bytes == info.slot_bytes and early == 1
                 assert tr * row_bytes <= sb_off and sb_off + 2 * tr * G * 2 <= slot_bytes
         assert 4096 + info.stages * info.slot_bytes < info.smem_bytes <= 224 * 1024
+
+
+def test_every_entry_point_is_documented():
+    """INTEGRATION.md names each exported function next to the reference call it replaces."""
+    from gbx_lm_b200 import _lib
+
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [n for n in _lib.EXPORTS if n not in text and n.replace("_string", "[_string]") not in text]
+    assert not missing, missing
