@@ -37,6 +37,7 @@ def lib():
         _lib.gbxq_oracle_dequantize.argtypes = [vp, vp, vp, vp, i64, i64, ci, ci, ci]
         _lib.gbxq_oracle_qmm.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, ci, ci, ci, ci, ci]
         _lib.gbxq_oracle_qmm_fast.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, ci, ci, ci, ci]
+        _lib.gbxq_oracle_quantize.argtypes = [vp, vp, vp, vp, i64, i64, ci, ci, ci]
         _lib.gbxq_oracle_max_threads.restype = ci
     return _lib
 
@@ -113,6 +114,19 @@ def qmm_fast(x, w, scales, biases, group_size, bits, nthreads=0):
     if rc:
         raise ValueError("oracle rejected the arguments")
     return y
+
+
+def quantize(w, group_size, bits, dtype="bf16"):
+    """w: [rows, K] raw array in `dtype` (uint16 bit patterns for bf16/f16).  Returns (codes uint32, scales, biases raw)."""
+    w = np.ascontiguousarray(w, dtype=_np_t(dtype))
+    rows, K = w.shape
+    q = np.zeros((rows, K * bits // 32), dtype=np.uint32)
+    s = np.zeros((rows, K // group_size), dtype=_np_t(dtype))
+    b = np.zeros((rows, K // group_size), dtype=_np_t(dtype))
+    rc = lib().gbxq_oracle_quantize(_p(w), _p(q), _p(s), _p(b), rows, K, bits, group_size, DTYPES[dtype])
+    if rc:
+        raise ValueError("oracle rejected the arguments")
+    return q, s, b
 
 
 def max_threads() -> int:

@@ -245,6 +245,58 @@ int gbxq_oracle_qmm_fast(const void* x, const uint32_t* w, const void* scales, c
     return 0;
 }
 
+/* ------------------------------------------------------------------ quantize */
+/* mx.quantize (MLX_SPEC R6), written as MLX's CPU quantiser walks a matrix (mlx/backend/cpu/quantized.cpp `quantize`,
+ * as recalled): one group at a time, fp32 statistics, the edge of larger magnitude anchored exactly, the codes from the
+ * UNROUNDED scale / bias, the statistics cast to T last.  Reached from the quantized KV cache,
+ * /root/reference/gbx_lm/models/cache.py:176-177,251-263.  rows x K values of T in, codes [rows, K*bits/32] out. */
+int gbxq_oracle_quantize(const void* w, uint32_t* q, void* scales, void* biases, int64_t rows, int64_t K, int bits,
+                         int gs, int dtype) {
+    if (!valid(bits, gs, K) || dtype < 0 || dtype > 2 || rows < 0) return -1;
+    const int64_t wpr = K * bits / 32, G = K / gs;
+    const float n_bins = (float)((1 << bits) - 1);
+    const float eps = 1e-7f;
+    memset(q, 0, (size_t)(rows * wpr) * 4);
+#pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < rows; r++) {
+        for (int64_t g = 0; g < G; g++) {
+            const int64_t base = r * K + g * gs;
+            float w_min = INFINITY, w_max = -INFINITY;
+            for (int j = 0; j < gs; j++) {
+                const float v = load_t(w, (size_t)(base + j), dtype);
+                w_max = v > w_max ? v : w_max;
+                w_min = v < w_min ? v : w_min;
+            }
+            const int mask = fabsf(w_min) > fabsf(w_max);
+            volatile float range = w_max - w_min;
+            float scale = range / n_bins;
+            scale = scale > eps ? scale : eps;
+            scale = mask ? scale : -scale;
+            const float edge = mask ? w_min : w_max;
+            const float q0 = rintf(edge / scale);
+            float bias = 0.0f;
+            if (q0 != 0.0f) {
+                scale = edge / q0;
+                bias = edge;
+            }
+            for (int j = 0; j < gs; j++) {
+                volatile float d = load_t(w, (size_t)(base + j), dtype) - bias;
+                float c = rintf(d / scale);
+                c = c < 0.0f ? 0.0f : (c > n_bins ? n_bins : c);
+                const uint64_t code = (uint64_t)(uint32_t)c;
+                const int64_t bit = (g * gs + j) * bits;
+                const int64_t wi = bit >> 5;
+                const int off = (int)(bit & 31);
+                q[r * wpr + wi] |= (uint32_t)(code << off);
+                if (off + bits > 32) q[r * wpr + wi + 1] |= (uint32_t)(code >> (32 - off));
+            }
+            store_t(scales, (size_t)(r * G + g), scale, dtype);
+            store_t(biases, (size_t)(r * G + g), bias, dtype);
+        }
+    }
+    return 0;
+}
+
 int gbxq_oracle_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

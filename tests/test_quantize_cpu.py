@@ -32,6 +32,29 @@ def test_quantize_numpy_vs_independent_scalar_checker(bits, dtype):
     assert (codes[0, :gs] == 0).all() and s[0, 0] == A._round_to(np.float32(-1e-7), dtype) and b[0, 0] == 0
 
 
+@pytest.mark.parametrize("dtype", ["bf16", "f16", "f32"])
+def test_quantize_numpy_vs_c_oracle(dtype):
+    """Second independent implementation: the C restatement walks the matrix group by group as MLX's CPU quantiser does
+    (oracle/gbxq_oracle.c::gbxq_oracle_quantize); codes and statistics equal the numpy one on every width x group size,
+    including zero / constant / one-sided groups and magnitudes from 1e-6 to 1e4."""
+    from oracle import c_oracle as C
+
+    rng = np.random.default_rng(3)
+    for bits in A.SUPPORTED_BITS:
+        for gs in (32, 64, 128):
+            w = rng.standard_normal((37, 3 * gs)).astype(np.float32) * rng.choice([1e-6, 1e-2, 1.0, 1e4], size=(37, 1)).astype(np.float32)
+            w[0, :gs] = 0.0
+            w[1, :gs] = -0.37
+            w[2, :gs] = np.abs(w[2, :gs])
+            w = A._round_to(w, dtype)
+            qn, sn, bn = A.quantize(w, gs, bits, dtype)
+            raw = w if dtype == "f32" else (A.f32_to_bf16_bits(w) if dtype == "bf16" else w.astype(np.float16).view(np.uint16))
+            qc, sc, bc = C.quantize(raw, gs, bits, dtype)
+            widen = (lambda a: a) if dtype == "f32" else (A.bf16_bits_to_f32 if dtype == "bf16" else (lambda a: a.view(np.float16).astype(np.float32)))
+            assert np.array_equal(qc, qn), (bits, gs)
+            assert np.array_equal(widen(sc), sn) and np.array_equal(widen(bc), bn), (bits, gs)
+
+
 @pytest.mark.parametrize("bits", A.SUPPORTED_BITS)
 def test_quantize_properties(bits):
     """What holds whatever the exact recipe (R6, last sentence): the anchored edge is exact, the error is at most one
