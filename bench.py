@@ -505,6 +505,9 @@ def run_gbxq(args):
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
+_CPU_BLOCK0: dict = {}
+
+
 def cpu_sample(args, layers_for_cpu=None, M=1, budget_s=12.0):
     """Times the CPU restatement of the reference path (oracle/gbxq_oracle.c, OpenMP) on a bounded
     sample: the 7 projections of block 0 of the workload, repeated until ~budget_s seconds."""
@@ -525,9 +528,13 @@ def cpu_sample(args, layers_for_cpu=None, M=1, budget_s=12.0):
                          m.scales.cpu().view(torch.int16).numpy().view(np.uint16),
                          m.zeros.cpu().view(torch.int16).numpy().view(np.uint16), m.bits, m.group_size))
     else:
-        for (i, p, n, k, b, g) in block0:
-            L = A.synth_layer(n, k, b, g, seed=i * 7 + len(data))
-            data.append((L["qweight"], L["scales"], L["zeros"], b, g))
+        key = (args.model, args.strategy, args.bits, args.group_size)
+        if key not in _CPU_BLOCK0:  # generated once per process: the reference arm samples the same block every step
+            _CPU_BLOCK0[key] = []
+            for (i, p, n, k, b, g) in block0:
+                L = A.synth_layer(n, k, b, g, seed=i * 7 + len(_CPU_BLOCK0[key]))
+                _CPU_BLOCK0[key].append((L["qweight"], L["scales"], L["zeros"], b, g))
+        data = _CPU_BLOCK0[key]
     xs = {k: A.synth_x(M, k, seed=3) for k in {d[0].shape[1] * 32 // d[3] for d in data}}
     threads = max(C.max_threads(), int(os.environ.get("GBXQ_CPU_THREADS", "0")))  # explicit omp_set_num_threads in the C call
     nbytes = sum(W.qmm_bytes(M, d[0].shape[0], d[0].shape[1] * 32 // d[3], d[3], d[4]) for d in data)
@@ -542,7 +549,7 @@ def cpu_sample(args, layers_for_cpu=None, M=1, budget_s=12.0):
         one_pass()
         passes += 1
         el = time.perf_counter() - t0
-        if el >= budget_s or passes >= 200:
+        if el >= budget_s or passes >= 5000:
             break
     per = el / passes
     return {"value": round(nbytes / per / 1e9, 3), "unit": UNIT, "cores": threads, "kind": "port",
@@ -566,7 +573,7 @@ def run_reference(args):
         r = cpu_sample(args, None, args.batch, budget_s=per_step_budget)
         if i >= args.warmup:
             vals.append(r)
-    v = statistics.median([r["value"] for r in vals])
+    v = round(statistics.median([r["value"] for r in vals]), 3)
     ms = statistics.median([r["ms_per_sample"] for r in vals])
     bytes_step = sum(W.qmm_bytes(args.batch, n, k, b, g) for (_, _, n, k, b, g) in plan)
     line = {
