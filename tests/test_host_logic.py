@@ -62,3 +62,25 @@ def test_traffic_json_reproducible_from_launch_list(tmp_path):
     assert sum(k["launches"] for k in got["kernels"].values()) == 128
     # no re-reads: DRAM traffic within 2 % of the algorithmic bytes of the step (bench.py config.bytes_per_step)
     assert 1.0 <= got["dram_read_bytes_step"] / 3461349376 < 1.02
+
+
+def test_switch_glu_sort_and_unsort_are_inverse():
+    """switch_layers.py:11-23 of the reference: (token, slot) pairs ordered by expert for the sorted gather_qmm path and
+    put back afterwards; the oracle-side statement of what SwitchGLU relies on (host logic, no kernel)."""
+    from gbx_lm_b200 import switch_layers as SL
+
+    gen = torch.Generator().manual_seed(0)
+    T, topk, H, E = 40, 2, 8, 5
+    x = torch.randn((1, T, 1, 1, H), generator=gen)
+    idx = torch.randint(0, E, (1, T, topk), generator=gen)
+    xs, flat, inv = SL._gather_sort(x, idx)
+    assert xs.shape == (T * topk, 1, H) and flat.shape == (T * topk,)
+    assert bool((flat[1:] >= flat[:-1]).all())                       # ordered by expert
+    # row j of the sorted activations is the token that owns pair order[j]
+    order = torch.argsort(idx.flatten(), stable=True)
+    assert torch.equal(xs, x.flatten(0, -3)[order // topk])
+    # a per-pair payload survives the round trip: y[pair] = (token, expert)
+    y = torch.stack([(order // topk).float(), flat.float()], -1)
+    back = SL._scatter_unsort(y, inv, idx.shape)
+    want = torch.stack([torch.arange(T).repeat_interleave(topk).float().reshape(1, T, topk), idx.float()], -1)
+    assert torch.equal(back, want)
