@@ -1,85 +1,127 @@
-"""The two KV caches either side of the quantized-KV attention path: `KVCache`
-(gbx_lm/models/cache.py:216-266) and `QuantizedKVCache` (cache.py:133-213), same attributes, growth rule (blocks of
-`step` = 256 positions), `state` / `meta_state` / `trim` semantics and `update_and_fetch` signature.
+"""The two KV caches either side of the quantized-KV attention path, with the interface of the
+reference's `KVCache` (gbx_lm/models/cache.py:216-266) and `QuantizedKVCache` (cache.py:133-213): attributes `keys`,
+`values`, `offset`, `step`, (`group_size`, `bits`), methods `update_and_fetch`, `state`, `meta_state`, `trim`,
+`is_trimmable`, `to_quantized`, and the same growth rule, so that a caller written against the reference
+(`maybe_quantize_kv_cache`, gbx_lm/utils.py:204-214; the attention layers) runs unchanged.
 
-What is new underneath: `mx.quantize` of the fresh keys / values (cache.py:176-177) plus the three slice assignments
-(cache.py:178-180) are ONE `gbxq_quantize_rows` launch per tensor that writes codes, scales and biases at the current
-offset of the cache buffers (ops.quantize_into); `KVCache.to_quantized` (cache.py:251-263) is `gbxq_quantize` on the
-whole prefix.  The consumer is `switch_layers.quantized_scaled_dot_product_attention` (gbx_lm/models/base.py:65-98).
-The decode path of `qllama.py` keeps its own static bf16 cache; these classes serve `maybe_quantize_kv_cache`-style
-callers (gbx_lm/utils.py:204-214).  CUDA only, like everything in this package."""
+Built differently underneath.  Both caches are one block-grown store (`_BlockStore`): tuples of position-major CUDA
+buffers `[B, H, capacity, width]` that share `offset`; the dense cache holds one buffer per side, the quantized one
+three (codes, scales, biases).  What the reference does with `mx.quantize` followed by three slice assignments per
+side (cache.py:176-180) is ONE `gbxq_quantize_rows` launch per side that writes codes and statistics at the offset
+(`ops.quantize_into`); `to_quantized` (cache.py:251-263) is `gbxq_quantize` over the buffers.  The consumer is
+`switch_layers.quantized_scaled_dot_product_attention` (gbx_lm/models/base.py:65-98).  The decode path of `qllama.py`
+keeps its own static bf16 cache.  CUDA only, like everything in this package."""
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Callable, Optional, Sequence, Tuple
 
 import torch
 
 from . import ops
 
 QTensor = Tuple[torch.Tensor, torch.Tensor, torch.Tensor]
+Bufs = Tuple[torch.Tensor, ...]
 
 
-class QuantizedKVCache:
-    """cache.py:133-213.  `keys` / `values` are (codes uint32 [B, H, cap, D*bits/32], scales, biases [B, H, cap,
-    D/group_size]) triples; `update_and_fetch` returns views of the first `offset` positions."""
+def _zeros(shape, dtype: torch.dtype, device) -> torch.Tensor:
+    # uint32 has few torch kernels: codes are allocated / concatenated as int32 and viewed
+    if dtype == torch.uint32:
+        return torch.zeros(shape, dtype=torch.int32, device=device).view(torch.uint32)
+    return torch.zeros(shape, dtype=dtype, device=device)
 
-    def __init__(self, group_size: int = 64, bits: int = 8):
-        self.keys: Optional[QTensor] = None
-        self.values: Optional[QTensor] = None
+
+def _cat_positions(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    if a.dtype == torch.uint32:
+        return torch.cat([a.view(torch.int32), b.view(torch.int32)], dim=-2).view(torch.uint32)
+    return torch.cat([a, b], dim=-2)
+
+
+class _BlockStore:
+    """`offset` valid positions in buffers that grow by whole blocks of `step` positions.
+
+    Growth rule (the reference's, cache.py:145-171 / 224-239, kept because `state` exposes the capacity): when the new
+    positions do not fit, ceil(new / step) blocks are appended -- after cutting the buffers back to `offset` if that is
+    not a block border."""
+
+    def __init__(self):
         self.offset = 0
         self.step = 256
+
+    @staticmethod
+    def _capacity(bufs: Optional[Bufs]) -> int:
+        return 0 if bufs is None else bufs[0].shape[-2]
+
+    def _make_room(self, sides: Sequence[Optional[Bufs]], new: int, fresh: Callable[[int], Sequence[Bufs]]):
+        """The sides (tuples of buffers) with room for `new` more positions; `fresh(n)` allocates n zeroed positions
+        of every buffer of every side."""
+        if sides[0] is not None and self.offset + new <= self._capacity(sides[0]):
+            return list(sides)
+        blocks = -(-new // self.step) * self.step
+        grown = []
+        for old, add in zip(sides, fresh(blocks)):
+            if old is None:
+                grown.append(tuple(add))
+                continue
+            cut = self.offset if self.offset % self.step else self._capacity(old)
+            grown.append(tuple(_cat_positions(o[..., :cut, :], a) for o, a in zip(old, add)))
+        return grown
+
+    def _valid(self, bufs: Bufs) -> Bufs:
+        return tuple(t[..., : self.offset, :] for t in bufs)
+
+    def is_trimmable(self) -> bool:
+        return True
+
+    def trim(self, n: int) -> int:
+        n = min(self.offset, n)
+        self.offset -= n
+        return n
+
+
+class QuantizedKVCache(_BlockStore):
+    """cache.py:133-213.  `keys` / `values` are (codes uint32 [B, H, capacity, D*bits/32], scales, biases [B, H,
+    capacity, D/group_size]) triples; `update_and_fetch` returns views of the first `offset` positions."""
+
+    def __init__(self, group_size: int = 64, bits: int = 8):
+        super().__init__()
+        self.keys: Optional[QTensor] = None
+        self.values: Optional[QTensor] = None
         self.group_size = group_size
         self.bits = bits
 
-    # the two device operations, overridable so that the growth / trim logic can be exercised without a GPU
+    # the device operation, overridable so that growth / trim / state can be exercised without a GPU
     @staticmethod
     def _quantize_into(x: torch.Tensor, out: QTensor, offset: int, group_size: int, bits: int) -> None:
         ops.quantize_into(x, out, offset, group_size, bits)
 
-    def _init_quant(self, shape, dim: int, dtype: torch.dtype, device) -> QTensor:
-        # the reference allocates dim // (32 // bits) words (cache.py:150,156), which is dim * bits / 32 for 2/4/8-bit and
-        # mis-sized for the straddling 3-/6-bit packings (32 // 3 = 10): the stream length is used here
-        words = dim * self.bits // 32
-        # uint32 has few torch kernels: allocate / concatenate as int32 and view
-        return (torch.zeros((*shape, words), dtype=torch.int32, device=device).view(torch.uint32),
-                torch.zeros((*shape, dim // self.group_size), dtype=dtype, device=device),
-                torch.zeros((*shape, dim // self.group_size), dtype=dtype, device=device))
+    def _fresh(self, lead, dims, like: torch.Tensor):
+        def alloc(n: int):
+            # D * bits / 32 words per position: the reference's D // (32 // bits) (cache.py:150,156) is the same for
+            # 2/4/8-bit and mis-sized for the straddling 3-/6-bit packings (32 // 3 = 10)
+            return [(_zeros((*lead, n, d * self.bits // 32), torch.uint32, like.device),
+                     _zeros((*lead, n, d // self.group_size), like.dtype, like.device),
+                     _zeros((*lead, n, d // self.group_size), like.dtype, like.device)) for d in dims]
+
+        return alloc
 
     def update_and_fetch(self, keys: torch.Tensor, values: torch.Tensor) -> Tuple[QTensor, QTensor]:
-        B, n_kv_heads, num_steps, k_head_dim = keys.shape
-        v_head_dim = values.shape[-1]
-        prev = self.offset
-        if self.keys is None or (prev + num_steps) > self.keys[0].shape[-2]:
-            new_steps = (self.step + num_steps - 1) // self.step * self.step
-            shape = (B, n_kv_heads, new_steps)
-            if self.keys is not None:
-                def expand(x: torch.Tensor) -> torch.Tensor:
-                    if prev % self.step != 0:
-                        x = x[..., :prev, :]
-                    codes = x.dtype == torch.uint32
-                    if codes:
-                        x = x.view(torch.int32)
-                    x = torch.cat([x, torch.zeros((*shape, x.shape[-1]), dtype=x.dtype, device=x.device)], dim=-2)
-                    return x.view(torch.uint32) if codes else x
-
-                self.keys = tuple(expand(x) for x in self.keys)
-                self.values = tuple(expand(x) for x in self.values)
-            else:
-                self.keys = self._init_quant(shape, k_head_dim, keys.dtype, keys.device)
-                self.values = self._init_quant(shape, v_head_dim, values.dtype, values.device)
-        if not all(x.is_contiguous() for x in (*self.keys, *self.values)):  # a `state` set from views
-            self.keys = tuple(x.contiguous() for x in self.keys)
-            self.values = tuple(x.contiguous() for x in self.values)
-        self.offset += num_steps
-        self._quantize_into(keys, self.keys, prev, self.group_size, self.bits)
-        self._quantize_into(values, self.values, prev, self.group_size, self.bits)
-        return (tuple(x[..., : self.offset, :] for x in self.keys), tuple(x[..., : self.offset, :] for x in self.values))
+        new = keys.shape[-2]
+        k_side, v_side = self._make_room((self.keys, self.values), new,
+                                         self._fresh(keys.shape[:-2], (keys.shape[-1], values.shape[-1]), keys))
+        # the kernel writes into the buffers in place: they must be dense (a `state` set from views is not)
+        self.keys = tuple(t if t.is_contiguous() else t.contiguous() for t in k_side)
+        self.values = tuple(t if t.is_contiguous() else t.contiguous() for t in v_side)
+        at = self.offset
+        self.offset = at + new
+        self._quantize_into(keys, self.keys, at, self.group_size, self.bits)
+        self._quantize_into(values, self.values, at, self.group_size, self.bits)
+        return self._valid(self.keys), self._valid(self.values)
 
     @property
     def state(self):
-        if self.offset == self.keys[0].shape[2]:
+        if self.offset == self._capacity(self.keys):
             return self.keys, self.values
-        return (tuple(x[..., : self.offset, :] for x in self.keys), tuple(x[..., : self.offset, :] for x in self.values))
+        return self._valid(self.keys), self._valid(self.values)
 
     @state.setter
     def state(self, v):
@@ -87,87 +129,64 @@ class QuantizedKVCache:
 
     @property
     def meta_state(self):
-        return tuple(map(str, (self.step, self.offset, self.group_size, self.bits)))
+        return tuple(str(v) for v in (self.step, self.offset, self.group_size, self.bits))
 
     @meta_state.setter
     def meta_state(self, v):
-        self.step, self.offset, self.group_size, self.bits = map(int, v)
-
-    def is_trimmable(self) -> bool:
-        return True
-
-    def trim(self, n: int) -> int:
-        n = min(self.offset, n)
-        self.offset -= n
-        return n
+        self.step, self.offset, self.group_size, self.bits = (int(s) for s in v)
 
 
-class KVCache:
+class KVCache(_BlockStore):
     """cache.py:216-266: the dense cache a prompt is processed into before `to_quantized`."""
 
     def __init__(self):
+        super().__init__()
         self.keys: Optional[torch.Tensor] = None
         self.values: Optional[torch.Tensor] = None
-        self.offset = 0
-        self.step = 256
 
     @staticmethod
     def _quantize(x: torch.Tensor, group_size: int, bits: int) -> QTensor:
         return ops.quantize(x, group_size, bits)
 
     def update_and_fetch(self, keys: torch.Tensor, values: torch.Tensor):
-        prev = self.offset
-        if self.keys is None or (prev + keys.shape[2]) > self.keys.shape[2]:
-            B, n_kv_heads, _, k_head_dim = keys.shape
-            v_head_dim = values.shape[3]
-            n_steps = (self.step + keys.shape[2] - 1) // self.step
-            new_k = torch.zeros((B, n_kv_heads, n_steps * self.step, k_head_dim), dtype=keys.dtype, device=keys.device)
-            new_v = torch.zeros((B, n_kv_heads, n_steps * self.step, v_head_dim), dtype=values.dtype, device=values.device)
-            if self.keys is not None:
-                if prev % self.step != 0:
-                    self.keys = self.keys[..., :prev, :]
-                    self.values = self.values[..., :prev, :]
-                self.keys = torch.cat([self.keys, new_k], dim=2)
-                self.values = torch.cat([self.values, new_v], dim=2)
-            else:
-                self.keys, self.values = new_k, new_v
-        self.offset += keys.shape[2]
-        self.keys[..., prev: self.offset, :] = keys
-        self.values[..., prev: self.offset, :] = values
-        return self.keys[..., : self.offset, :], self.values[..., : self.offset, :]
+        new = keys.shape[-2]
+
+        def fresh(n: int):
+            return [(_zeros((*t.shape[:-2], n, t.shape[-1]), t.dtype, t.device),) for t in (keys, values)]
+
+        sides = self._make_room([None if t is None else (t,) for t in (self.keys, self.values)], new, fresh)
+        self.keys, self.values = sides[0][0], sides[1][0]
+        at = self.offset
+        self.offset = at + new
+        self.keys[..., at: self.offset, :] = keys
+        self.values[..., at: self.offset, :] = values
+        return self._valid((self.keys, self.values))
 
     @property
     def state(self):
-        if self.offset == self.keys.shape[2]:
+        if self.offset == self.keys.shape[-2]:
             return self.keys, self.values
-        return self.keys[..., : self.offset, :], self.values[..., : self.offset, :]
+        return self._valid((self.keys, self.values))
 
     @state.setter
     def state(self, v):
         self.keys, self.values = v
-        self.offset = self.keys.shape[2]
-
-    def is_trimmable(self) -> bool:
-        return True
-
-    def trim(self, n: int) -> int:
-        n = min(self.offset, n)
-        self.offset -= n
-        return n
+        self.offset = self.keys.shape[-2]
 
     def to_quantized(self, group_size: int = 64, bits: int = 4) -> QuantizedKVCache:
-        quant_cache = QuantizedKVCache(group_size=group_size, bits=bits)
-        quant_cache.offset = self.offset
+        """The whole buffers are quantized (unused positions are zero groups), `offset` carries over."""
+        q = QuantizedKVCache(group_size=group_size, bits=bits)
+        q.offset = self.offset
         if self.keys is not None:
-            quant_cache.keys = self._quantize(self.keys, group_size, bits)
-            quant_cache.values = self._quantize(self.values, group_size, bits)
-        return quant_cache
+            q.keys = self._quantize(self.keys, group_size, bits)
+            q.values = self._quantize(self.values, group_size, bits)
+        return q
 
 
-def maybe_quantize_kv_cache(prompt_cache, quantized_kv_start: int, kv_group_size: int, kv_bits: Optional[int]) -> None:
-    """gbx_lm/utils.py:204-214: once the prompt is past `quantized_kv_start`, swap every dense cache for its
-    quantized form (in place in the list)."""
-    if kv_bits is not None and not isinstance(prompt_cache[0], QuantizedKVCache) and prompt_cache[0].offset > quantized_kv_start:
-        for i in range(len(prompt_cache)):
-            if isinstance(prompt_cache[i], KVCache):
-                prompt_cache[i] = prompt_cache[i].to_quantized(group_size=kv_group_size, bits=kv_bits)
+def maybe_quantize_kv_cache(prompt_cache: list, quantized_kv_start: int, kv_group_size: int, kv_bits: Optional[int]) -> None:
+    """gbx_lm/utils.py:204-214: once the prompt is longer than `quantized_kv_start`, every dense cache of the list is
+    replaced by its quantized form (the list is edited in place; a list that already starts quantized is left alone)."""
+    if kv_bits is None or isinstance(prompt_cache[0], QuantizedKVCache) or prompt_cache[0].offset <= quantized_kv_start:
+        return
+    prompt_cache[:] = [c.to_quantized(group_size=kv_group_size, bits=kv_bits) if isinstance(c, KVCache) else c
+                       for c in prompt_cache]
