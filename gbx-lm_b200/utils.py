@@ -46,14 +46,11 @@ def _get_classes(config: dict):
 
 
 def get_parameter_usage_info(weights: Dict[str, Any]) -> Tuple[bool, bool]:
-    """gbx_lm/utils.py:696-719."""
-    use_double_quantization = use_q_perm = False
-    for k in weights:
-        if any(t in k for t in ("qstatistic", "qscales_scales", "qzeros_scales", "qscales_zeros", "qzeros_zeros")):
-            use_double_quantization = True
-        if "q_perm" in k:
-            use_q_perm = True
-    return use_double_quantization, use_q_perm
+    """(double-quantised statistics present, q_perm present) -- gbx_lm/utils.py:696-719; one implementation, shared
+    with the converter."""
+    from .gba_convert import parameter_usage
+
+    return parameter_usage(weights)
 
 
 def _load_safetensors(path: str) -> Dict[str, torch.Tensor]:
