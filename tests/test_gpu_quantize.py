@@ -40,6 +40,27 @@ def test_quantize_bit_exact(cuda_device, bits, dtype):
             _check(w, ops.quantize(w, gs, bits), gs, bits, dtype, f"b{bits} g{gs} {dtype} {shape}")
 
 
+import json  # noqa: E402
+import os  # noqa: E402
+
+QG = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "quantize_golden.json")))
+
+
+@pytest.mark.parametrize("case", QG["cases"], ids=lambda c: f"b{c['bits']}-g{c['group_size']}")
+def test_quantize_golden_fixture(cuda_device, case):
+    """The committed known answers (written by the C restatement, tests/golden/make_quantize_golden.py)."""
+    from gbx_lm_b200 import ops
+
+    rows, K, bits, gs = case["rows"], case["K"], case["bits"], case["group_size"]
+    wb = np.array(case["w_bf16"], dtype=np.uint16).reshape(rows, K)
+    w = torch.from_numpy(wb.view(np.int16)).view(torch.bfloat16).to(cuda_device)
+    q, s, b = ops.quantize(w, gs, bits)
+    assert np.array_equal(_u32(q).reshape(-1), np.array(case["codes"], dtype=np.uint32))
+    bits16 = lambda t: t.detach().cpu().contiguous().view(torch.int16).numpy().view(np.uint16).reshape(-1)  # noqa: E731
+    assert np.array_equal(bits16(s), np.array(case["scales_bf16"], dtype=np.uint16))
+    assert np.array_equal(bits16(b), np.array(case["biases_bf16"], dtype=np.uint16))
+
+
 @pytest.mark.parametrize("bits", A.SUPPORTED_BITS)
 def test_quantize_special_groups(cuda_device, bits):
     """Zero and constant groups, one-sided groups (all negative / all positive), an outlier, magnitudes from 1e-30 to

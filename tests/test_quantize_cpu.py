@@ -55,6 +55,38 @@ def test_quantize_numpy_vs_c_oracle(dtype):
             assert np.array_equal(widen(sc), sn) and np.array_equal(widen(bc), bn), (bits, gs)
 
 
+def test_quantize_hand_derived_known_answers():
+    """Two groups whose answer follows from R6 by hand.  w = k mod 16 at 4 bits: max 15, min 0, |min| <= |max| so the
+    scale is negative, -(15 / 15) = -1; the edge is the maximum, q0 = rint(15 / -1) = -15, scale = 15 / -15 = -1,
+    bias = 15, code = rint((w - 15) / -1) = 15 - w.  Its mirror image w = -(k mod 16): |min| > |max|, scale = +1,
+    edge = -15, bias = -15, code = w + 15 -- the same codes."""
+    k = np.arange(64)
+    for sign, scale, bias in ((1.0, -1.0, 15.0), (-1.0, 1.0, -15.0)):
+        w = (sign * (k % 16)).astype(np.float32)[None]
+        q, s, b = A.quantize(w, 64, 4, "bf16")
+        assert s[0, 0] == scale and b[0, 0] == bias
+        assert (A.unpack_codes(q, 4)[0] == 15 - (k % 16)).all()
+        assert q[0, 0] == 0x89ABCDEF and q[0, 1] == 0x01234567   # codes 15..8 then 7..0, first code in the low nibble
+        assert I.quantize_group([float(v) for v in w[0]], 4) == (list(15 - (k % 16)), scale, bias)
+
+
+import json  # noqa: E402
+import os  # noqa: E402
+
+QG = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "quantize_golden.json")))
+
+
+@pytest.mark.parametrize("case", QG["cases"], ids=lambda c: f"b{c['bits']}-g{c['group_size']}")
+def test_quantize_golden_fixture(case):
+    """tests/golden/quantize_golden.json was written by the C restatement; the numpy oracle reproduces it."""
+    rows, K, bits, gs = case["rows"], case["K"], case["bits"], case["group_size"]
+    w = A.bf16_bits_to_f32(np.array(case["w_bf16"], dtype=np.uint16).reshape(rows, K))
+    q, s, b = A.quantize(w, gs, bits, "bf16")
+    assert np.array_equal(q.reshape(-1), np.array(case["codes"], dtype=np.uint32))
+    assert np.array_equal(A.f32_to_bf16_bits(s).reshape(-1), np.array(case["scales_bf16"], dtype=np.uint16))
+    assert np.array_equal(A.f32_to_bf16_bits(b).reshape(-1), np.array(case["biases_bf16"], dtype=np.uint16))
+
+
 @pytest.mark.parametrize("bits", A.SUPPORTED_BITS)
 def test_quantize_properties(bits):
     """What holds whatever the exact recipe (R6, last sentence): the anchored edge is exact, the error is at most one
