@@ -256,3 +256,40 @@ def test_expand_statistics_of_an_mlx_oriented_double_quant_checkpoint():
     assert set(out) == {p + "qweight", p + "scales", p + "zeros"}
     assert torch.equal(out[p + "qweight"], w[p + "qweight"])
     assert np.array_equal(out[p + "scales"].float().numpy(), s_bf.T) and np.array_equal(out[p + "zeros"].float().numpy(), z_bf.T)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the reference's own two tests of this area (/root/reference/tests/test_utils.py:27-54), restated for this loader
+# ---------------------------------------------------------------------------------------------------------------
+def test_load_eager_and_lazy_agree(tiny_ckpt):
+    """test_utils.py:27-36 (`test_load`): the same qweight whether the model is loaded eagerly or lazily."""
+    d, _, _ = tiny_ckpt
+    model, _ = utils.load(d, device="cpu")
+    model_lazy, _ = utils.load(d, lazy=True, device="cpu")
+    p1 = model.model.layers[0].mlp.up_proj.qweight
+    p2 = model_lazy.model.layers[0].mlp.up_proj.qweight
+    assert torch.equal(p1.view(torch.int32), p2.view(torch.int32))
+
+
+def test_make_shards_count_follows_the_byte_total():
+    """test_utils.py:38-54 (`test_make_shards`): with a 1 GiB cap the number of files is the model's size in GiB or one
+    more.  Same dimensions as the reference's test (hidden 2048, 32 layers, intermediate 4096, vocabulary 30 000),
+    dense fp32 tensors on the meta device (only sizes matter)."""
+    h, layers, inter, vocab = 2048, 32, 4096, 30_000
+    meta = lambda *shape: torch.empty(shape, dtype=torch.float32, device="meta")  # noqa: E731
+    w = {"model.embed_tokens.weight": meta(vocab, h), "lm_head.weight": meta(vocab, h), "model.norm.weight": meta(h)}
+    for i in range(layers):
+        p = f"model.layers.{i}."
+        for n in ("q_proj", "k_proj", "v_proj", "o_proj"):
+            w[p + f"self_attn.{n}.weight"] = meta(h, h)
+        w[p + "mlp.gate_proj.weight"] = meta(inter, h)
+        w[p + "mlp.up_proj.weight"] = meta(inter, h)
+        w[p + "mlp.down_proj.weight"] = meta(h, inter)
+        w[p + "input_layernorm.weight"] = meta(h)
+        w[p + "post_attention_layernorm.weight"] = meta(h)
+    gb = sum(t.numel() * t.element_size() for t in w.values()) // 2 ** 30
+    shards = utils.make_shards(w, 1)
+    assert gb >= 5 and gb <= len(shards) <= gb + 1
+    assert sum(len(s) for s in shards) == len(w) and all(s for s in shards)
+    cap = 1 << 30
+    assert all(sum(t.numel() * t.element_size() for t in s.values()) <= cap for s in shards)
