@@ -274,3 +274,29 @@ def test_kv_cache_to_quantized_and_maybe_quantize(stubbed_caches):
     big = torch.zeros((1, 2, 300, 64), dtype=torch.bfloat16)
     d.update_and_fetch(big, big)                          # 16 + 300 > 256: cut at prev (16 % 256 != 0), add two blocks
     assert d.offset == 316 and d.keys.shape[2] == 16 + 512
+
+
+def test_cache_and_attention_flow_with_oracle_backed_ops(monkeypatch):
+    """The body of the GPU test of the quantized cache + attention (tests/test_gpu_quantize.py) with the three device
+    operations replaced by the oracle on the CPU: everything around the kernels -- cache growth across the block border,
+    views handed to the attention wrapper, GQA reshapes, softmax, `to_quantized` -- is the code the GPU run executes."""
+    from gbx_lm_b200 import ops
+    import tests.test_gpu_quantize as T
+
+    def deq(w, s, b, gs, bits):
+        d = A.dequantize(w.contiguous().view(torch.int32).numpy().view(np.uint32).reshape(-1, w.shape[-1]),
+                         s.float().numpy().reshape(-1, s.shape[-1]), b.float().numpy().reshape(-1, b.shape[-1]), gs, bits, "f32")
+        return torch.from_numpy(d).reshape(*w.shape[:-1], -1)
+
+    def qmm(x, w, s, b, transpose=True, group_size=64, bits=4, **kw):
+        W = deq(w, s, b, group_size, bits)
+        return (x.float() @ (W.transpose(-1, -2) if transpose else W)).to(x.dtype)
+
+    def quantize_into(x, out, offset, group_size, bits):
+        assert all(t.is_contiguous() for t in out)       # what gbxq_quantize_rows requires of the cache buffers
+        _oracle_quantize_into(x.contiguous(), out, offset, group_size, bits)
+
+    monkeypatch.setattr(ops, "quantize", _oracle_quantize)
+    monkeypatch.setattr(ops, "quantize_into", quantize_into)
+    monkeypatch.setattr(ops, "quantized_matmul", qmm)
+    T.test_quantized_kv_cache_and_attention_on_device(torch.device("cpu"))
